@@ -1,0 +1,17 @@
+"""boatenv-b200: B200-native batched BoatEnv step path behind the reference's gym-style API.
+
+    from sac_agent_b200 import BatchedBoatEnv, BoatEnv, ReplayBuffer, load_config
+
+Everything that computes runs in hand-written sm_100a CUDA kernels inside
+``libboatenv.so`` (C ABI: ``include/boatenv.h``).  There is no CPU fallback: importing
+the env classes works anywhere, constructing one without the library or without a GPU
+raises.
+"""
+from .config import AttrDict, load_config, params_from_config  # noqa: F401
+from ._lib import BoatEnvError, lib, library_path  # noqa: F401
+from .boat_env import BatchedBoatEnv, BoatEnv, Box, TERM_NAMES  # noqa: F401
+from .buffer import ReplayBuffer  # noqa: F401
+from .toy_envs import ToyCar, ToyParachute  # noqa: F401
+
+__all__ = ["AttrDict", "load_config", "params_from_config", "BoatEnvError", "lib", "library_path",
+           "BatchedBoatEnv", "BoatEnv", "Box", "TERM_NAMES", "ReplayBuffer", "ToyCar", "ToyParachute"]

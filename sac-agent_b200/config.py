@@ -1,0 +1,83 @@
+"""original_config.yaml semantics (utils/config_reader.py:6-14 of the reference).
+
+The reference reads its YAML into a ``DotMap``; ``AttrDict`` offers the same attribute
+access, and every entry point here also accepts a real DotMap or a plain dict.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import yaml
+
+DEFAULT_CONFIG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "original_config.yaml")
+
+
+class AttrDict(dict):
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+        if isinstance(v, dict) and not isinstance(v, AttrDict):
+            v = AttrDict(v)
+            self[k] = v
+        return v
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def load_config(path: str | None = None, **overrides) -> AttrDict:
+    """get_config (utils/config_reader.py:6-8).  ``overrides``: section__key=value."""
+    with open(path or DEFAULT_CONFIG) as f:
+        cfg = yaml.safe_load(f)
+    for k, v in overrides.items():
+        sec, key = k.split("__", 1)
+        cfg[sec][key] = v
+    return AttrDict(cfg)
+
+
+class BoatEnvParams(C.Structure):
+    """Mirror of ``boatenv_params`` (include/boatenv.h)."""
+    _fields_ = [
+        ("experiment", C.c_int32), ("test_mode", C.c_int32),
+        ("dt", C.c_double), ("t_max", C.c_double),
+        ("track_width", C.c_double), ("oob_offset", C.c_double), ("goal_line", C.c_double),
+        ("fuel", C.c_double),
+        ("boat_m", C.c_double), ("boat_m_x", C.c_double), ("boat_m_y", C.c_double),
+        ("boat_I", C.c_double), ("boat_Iz", C.c_double),
+        ("propeller_diameter", C.c_double), ("wake_friction", C.c_double),
+        ("c_r_front", C.c_double), ("c_r_side", C.c_double), ("thrust_deduction", C.c_double),
+        ("rho", C.c_double), ("boat_area_front", C.c_double), ("boat_area_side", C.c_double),
+        ("boat_l", C.c_double), ("boat_b", C.c_double), ("rudder_area", C.c_double),
+        ("fixed_points", C.c_int32), ("_pad", C.c_int32),
+        ("max_velocity", C.c_double), ("direction", C.c_double),
+    ]
+
+
+def _get(cfg, sec, key):
+    s = cfg[sec] if isinstance(cfg, dict) else getattr(cfg, sec)
+    return s[key] if isinstance(s, dict) else getattr(s, key)
+
+
+def params_from_config(cfg) -> BoatEnvParams:
+    """The keys the hot path reads; everything else is ignored,
+    as in the reference."""
+    p = BoatEnvParams()
+    p.experiment = int(_get(cfg, "base_settings", "experiment"))  # wind.py:30 int(...)
+    p.test_mode = int(_get(cfg, "base_settings", "test_mode"))
+    p.dt = float(_get(cfg, "base_settings", "dt"))
+    p.t_max = float(_get(cfg, "base_settings", "t_max"))
+    p.track_width = float(_get(cfg, "boat_env", "track_width"))
+    p.oob_offset = float(_get(cfg, "boat_env", "boat_out_of_bounds_offset"))
+    p.goal_line = float(_get(cfg, "boat_env", "goal_line"))
+    p.fuel = float(_get(cfg, "boat", "fuel"))
+    for k in ("boat_m", "boat_m_x", "boat_m_y", "boat_I", "boat_Iz", "propeller_diameter",
+              "wake_friction", "c_r_front", "c_r_side", "thrust_deduction", "rho",
+              "boat_area_front", "boat_area_side", "boat_l", "boat_b", "rudder_area"):
+        setattr(p, k, float(_get(cfg, "boat", k)))
+    p.fixed_points = int(_get(cfg, "wind", "fixed_points"))
+    p.max_velocity = float(_get(cfg, "wind", "max_velocity"))
+    p.direction = float(_get(cfg, "wind", "direction"))
+    return p

@@ -1,0 +1,501 @@
+// abi.cu -- the extern "C" front end of libboatenv.so (include/boatenv.h): handle
+// management, config derivation, launches.  No compute happens on the host.
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "launch.h"
+
+using namespace boatenv;
+
+#define CUDA_TRY(expr)                                  \
+    do {                                                \
+        cudaError_t _e = (expr);                        \
+        if (_e != cudaSuccess) return (int)_e;          \
+    } while (0)
+
+namespace boatenv {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace boatenv
+
+struct boatenv_handle {
+    DevCfg cfg;
+    int precision, device;
+    size_t esize;
+    bool was_reset;
+    double *basis_dev;
+    int32_t *ovr_s_y;
+    double *ovr_knots;
+    double *counters_out_dev;  // 8 doubles
+    // step_host staging
+    void *h_act, *h_obs, *h_rew;
+    uint8_t *h_done;
+    cudaStream_t copy_in, compute, copy_out;
+    cudaEvent_t ev_in[8], ev_k[8];
+    bool host_path_ready;
+};
+
+// ---------------------------------------------------------------------------------
+// Cardinal basis of the not-a-knot cubic spline through `fp` uniform knots (the curve
+// scipy's interp1d(kind='cubic') builds at wind.py:82-84), per piece in the local
+// coordinate s in [0,1]:  coefficient m of piece j = sum_k basis[(j*4+m)*fp + k] * y_k.
+// Dimensionless moments m_i = h^2 S''(x_i) solve
+//   m_0 - 2 m_1 + m_2 = 0,  m_{i-1}/6 + 2 m_i/3 + m_{i+1}/6 = y_{i-1} - 2 y_i + y_{i+1},
+//   m_{n-3} - 2 m_{n-2} + m_{n-1} = 0.
+// ---------------------------------------------------------------------------------
+static void compute_spline_basis(int fp, std::vector<double> &basis) {
+    const int n = fp;
+    basis.assign((size_t)(n - 1) * 4 * n, 0.0);
+    std::vector<double> A((size_t)n * n), rhs(n), m(n);
+    for (int k = 0; k < n; ++k) {
+        std::fill(A.begin(), A.end(), 0.0);
+        std::vector<double> y(n, 0.0);
+        y[k] = 1.0;
+        A[0] = 1.0; A[1] = -2.0; A[2] = 1.0; rhs[0] = 0.0;
+        for (int i = 1; i < n - 1; ++i) {
+            A[(size_t)i * n + i - 1] = 1.0 / 6.0;
+            A[(size_t)i * n + i] = 2.0 / 3.0;
+            A[(size_t)i * n + i + 1] = 1.0 / 6.0;
+            rhs[i] = y[i - 1] - 2.0 * y[i] + y[i + 1];
+        }
+        A[(size_t)(n - 1) * n + n - 3] = 1.0; A[(size_t)(n - 1) * n + n - 2] = -2.0;
+        A[(size_t)(n - 1) * n + n - 1] = 1.0; rhs[n - 1] = 0.0;
+        for (int c = 0; c < n; ++c) {  // Gaussian elimination, partial pivoting
+            int piv = c;
+            for (int r = c + 1; r < n; ++r)
+                if (std::fabs(A[(size_t)r * n + c]) > std::fabs(A[(size_t)piv * n + c])) piv = r;
+            if (piv != c) {
+                for (int q = 0; q < n; ++q) std::swap(A[(size_t)c * n + q], A[(size_t)piv * n + q]);
+                std::swap(rhs[c], rhs[piv]);
+            }
+            for (int r = c + 1; r < n; ++r) {
+                const double f = A[(size_t)r * n + c] / A[(size_t)c * n + c];
+                for (int q = c; q < n; ++q) A[(size_t)r * n + q] -= f * A[(size_t)c * n + q];
+                rhs[r] -= f * rhs[c];
+            }
+        }
+        for (int r = n - 1; r >= 0; --r) {
+            double s = rhs[r];
+            for (int q = r + 1; q < n; ++q) s -= A[(size_t)r * n + q] * m[q];
+            m[r] = s / A[(size_t)r * n + r];
+        }
+        for (int j = 0; j < n - 1; ++j) {
+            const double c0 = y[j];
+            const double c1 = (y[j + 1] - y[j]) - (2.0 * m[j] + m[j + 1]) / 6.0;
+            const double c2 = m[j] / 2.0;
+            const double c3 = (m[j + 1] - m[j]) / 6.0;
+            basis[((size_t)j * 4 + 0) * n + k] = c0;
+            basis[((size_t)j * 4 + 1) * n + k] = c1;
+            basis[((size_t)j * 4 + 2) * n + k] = c2;
+            basis[((size_t)j * 4 + 3) * n + k] = c3;
+        }
+    }
+}
+
+static int derive_config(const boatenv_params *p, DevCfg &c) {
+    const double PI = 3.14159265358979323846;
+    std::memset(&c, 0, sizeof(c));
+    c.p = *p;
+    c.experiment = p->experiment;
+    c.test_mode = p->test_mode;
+    switch (p->experiment) {  // wind.py:30-67
+    case 1: case 2: c.wind_kind = WIND_NONE; c.ncurves = 0; break;
+    case 3: c.wind_kind = WIND_CONST; c.ncurves = 0; break;
+    case 4: c.wind_kind = WIND_VEL_CURVE; c.ncurves = 1; break;
+    case 5: c.wind_kind = WIND_ANGLE_RECT; c.ncurves = 1; break;
+    case 6: c.wind_kind = WIND_BOTH; c.ncurves = 2; break;
+    default: return BOATENV_EEXPERIMENT;
+    }
+    if (!(p->dt > 0.0) || !(p->t_max > 0.0) || !(p->track_width > 0.0) || !(p->fuel != 0.0)) return BOATENV_EINVAL;
+    c.fp = p->fixed_points;
+    if (c.ncurves > 0) {
+        if (c.fp < 4) return BOATENV_EFIXEDPOINTS;  // wind.py:73-75
+        if (c.fp > kMaxKnots) return BOATENV_EUNSUPPORTED;
+    } else if (c.fp < 2 || c.fp > kMaxKnots) {
+        c.fp = 8;  // unused without random curves
+    }
+    c.npieces = c.fp - 1;
+    const double Ld = p->t_max / p->dt;  // wind.py:14-15
+    if (!(Ld >= 2.0) || Ld > 16777216.0) return BOATENV_EUNSUPPORTED;
+    c.L = (int)Ld;
+    c.Lm1 = c.L - 1;
+    {   // boat_env.py:69,98: t accumulates dt; timeout at the first step with t_max <= t
+        double t = 0.0;
+        int n = 0;
+        while (n < c.L + 16) { t += p->dt; ++n; if (p->t_max <= t) break; }
+        c.timeout_steps = n;
+    }
+    c.s_y_half = (int)(p->track_width * 0.8);  // boat_env.py:148-149
+    if (c.s_y_half < 1) c.s_y_half = 1;
+    c.direction_rad = p->direction * (PI / 180.0);
+    c.prop_d4 = std::pow(p->propeller_diameter, 4.0);
+
+    FastConsts &f = c.f;
+    const double n = 20.0;
+    f.dt = (float)p->dt;
+    f.tenth = 0.1f;
+    const double kdx = p->c_r_front * 0.5 * p->rho * p->boat_area_front;
+    const double kdy = p->c_r_side * 0.5 * p->rho * p->boat_area_side;
+    f.kdx = (float)kdx;
+    f.kJ = (float)((1.0 - p->wake_friction) / (n * p->propeller_diameter));
+    f.kT = (float)(n * n * p->rho * c.prop_d4 * (1.0 - p->thrust_deduction));
+    f.cxy = (float)(p->boat_m + p->boat_m_y);
+    f.inv_mx = (float)(1.0 / (p->boat_m + p->boat_m_x));
+    f.kdy = (float)kdy;
+    f.kru = (float)(p->c_r_front * 0.5 * p->rho * p->rudder_area);
+    f.cyx = (float)(p->boat_m + p->boat_m_x);
+    f.inv_my = (float)(1.0 / (p->boat_m + p->boat_m_y));
+    f.kh = (float)(kdy * p->boat_l * 5.0);
+    f.kmr = (float)(p->c_r_side * 0.5 * p->rho * p->rudder_area * (p->boat_b / 2.0));
+    f.inv_I = (float)(1.0 / (p->boat_I + p->boat_Iz));
+    f.kwx = (float)kdx;
+    f.kwy = (float)kdy;
+    const double wv = p->max_velocity, ww = wv * std::fabs(wv);
+    f.fwx_c = (float)(ww * kdx * std::cos(c.direction_rad));
+    f.fwy_c = (float)(ww * kdy * std::sin(c.direction_rad));
+    f.cos_dir = (float)std::cos(c.direction_rad);
+    f.sin_dir = (float)std::sin(c.direction_rad);
+    const double th_lo = PI / 2.0, th_hi = PI + PI / 2.0;  // wind.py:57-58
+    f.fwx_lo = (float)(ww * kdx * std::cos(th_lo));
+    f.fwy_lo = (float)(ww * kdy * std::sin(th_lo));
+    f.fwx_hi = (float)(ww * kdx * std::cos(th_hi));
+    f.fwy_hi = (float)(ww * kdy * std::sin(th_hi));
+    f.inv_goal = (float)(1.0 / p->goal_line);
+    f.inv_5 = 0.2f;
+    f.inv_ax = (float)(1.0 / 0.025);
+    f.W = (float)p->track_width;
+    f.inv_2W = (float)(1.0 / (2.0 * p->track_width));
+    f.inv_2 = 0.5f;
+    f.inv_ay = (float)(1.0 / 0.37);
+    f.inv_2pi = (float)(1.0 / (2.0 * PI));
+    f.inv_vr = (float)(1.0 / 8.5e-3);
+    f.inv_ar = (float)(1.0 / 1.4e-5);
+    f.third_pi = (float)(PI / 3.0);
+    f.inv_rud = (float)(1.0 / (2.0 * PI / 3.0));
+    f.inv_fuel = (float)(1.0 / p->fuel);
+    f.fuel0 = (float)p->fuel;
+    f.goal = (float)p->goal_line;
+    f.oob = (float)(p->track_width + p->oob_offset);
+    f.pi3 = (float)(PI / 3.0);
+    f.pi4 = (float)(PI / 4.0);
+    f.pi2 = (float)(PI / 2.0);
+    f.rew_inv_W = (float)(1.0 / p->track_width);
+    f.rew_k = (float)(-0.03 / 3.4);
+    f.rew_y0 = (float)(p->track_width * 0.2);
+    return BOATENV_OK;
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" {
+
+const char *boatenv_version(void) { return "boatenv-b200 0.1 (sm_100a)"; }
+
+const char *boatenv_error_string(int code) {
+    switch (code) {
+    case BOATENV_OK: return "ok";
+    case BOATENV_EINVAL: return "invalid argument";
+    case BOATENV_EEXPERIMENT: return "Well someone tried to use an experiment that doesnt exist!";
+    case BOATENV_EFIXEDPOINTS:
+        return "Please select at least 4 fixed_points in your config. The interpolation doesn't work otherwise!";
+    case BOATENV_EUNSUPPORTED: return "configuration valid for the reference but unsupported by this build";
+    case BOATENV_ENODEVICE: return "no usable CUDA device";
+    case BOATENV_ESTATE: return "step() called before reset()";
+    case BOATENV_EALIGN: return "tensor pointer is not 16-byte aligned";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int64_t boatenv_kernel_launches(void) { return (int64_t)g_launches.load(); }
+
+int boatenv_create(const boatenv_params *params, int64_t n_envs, uint64_t seed, int64_t env_id_offset,
+                   int precision, int device, boatenv_t *out) {
+    if (!params || !out || n_envs <= 0 || env_id_offset < 0) return BOATENV_EINVAL;
+    if (precision != 32 && precision != 64) return BOATENV_EINVAL;
+    *out = nullptr;
+    DevCfg cfg;
+    int rc = derive_config(params, cfg);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return BOATENV_ENODEVICE;
+    CUDA_TRY(cudaSetDevice(device));
+    boatenv_handle *h = new (std::nothrow) boatenv_handle();
+    if (!h) return BOATENV_EINVAL;
+    std::memset(h, 0, sizeof(*h));
+    h->precision = precision;
+    h->device = device;
+    h->esize = precision == 32 ? 4 : 8;
+    cfg.n_envs = n_envs;
+    cfg.env_id_offset = env_id_offset;
+    cfg.seed = seed;
+    const size_t n = (size_t)n_envs;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    alloc(&cfg.dyn, n * D_COUNT * h->esize);
+    alloc((void **)&cfg.idx, n * sizeof(uint2));
+    if (cfg.ncurves >= 1) alloc(&cfg.windA, n * 4 * h->esize);
+    if (cfg.ncurves >= 2) alloc(&cfg.windB, n * 4 * h->esize);
+    alloc((void **)&cfg.counters, kCounterSlots * 32 * sizeof(double));
+    alloc((void **)&h->counters_out_dev, kNumCounters * sizeof(double));
+    std::vector<double> basis;
+    compute_spline_basis(cfg.fp, basis);
+    alloc((void **)&h->basis_dev, basis.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(h->basis_dev, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(cfg.dyn, 0, n * D_COUNT * h->esize);
+    if (e == cudaSuccess) e = cudaMemset(cfg.idx, 0xFF, n * sizeof(uint2));  // episode -1: reset() makes it 0
+    if (e == cudaSuccess) e = cudaMemset(cfg.counters, 0, kCounterSlots * 32 * sizeof(double));
+    cfg.basis = h->basis_dev;
+    h->cfg = cfg;
+    if (e != cudaSuccess) {
+        boatenv_destroy(h);
+        return (int)e;
+    }
+    *out = h;
+    return BOATENV_OK;
+}
+
+int boatenv_destroy(boatenv_t h) {
+    if (!h) return BOATENV_EINVAL;
+    cudaSetDevice(h->device);
+    cudaFree(h->cfg.dyn);
+    cudaFree(h->cfg.idx);
+    cudaFree(h->cfg.windA);
+    cudaFree(h->cfg.windB);
+    cudaFree(h->cfg.counters);
+    cudaFree(h->counters_out_dev);
+    cudaFree(h->basis_dev);
+    cudaFree(h->ovr_s_y);
+    cudaFree(h->ovr_knots);
+    cudaFree(h->h_act);
+    cudaFree(h->h_obs);
+    cudaFree(h->h_rew);
+    cudaFree(h->h_done);
+    if (h->host_path_ready) {
+        cudaStreamDestroy(h->copy_in);
+        cudaStreamDestroy(h->compute);
+        cudaStreamDestroy(h->copy_out);
+        for (int i = 0; i < 8; ++i) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
+    }
+    delete h;
+    return BOATENV_OK;
+}
+
+int boatenv_reset(boatenv_t h, const uint8_t *mask, void *obs_out, void *stream) {
+    if (!h) return BOATENV_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h->precision == 32 ? launch_reset_f32(h->cfg, mask, obs_out, st)
+                                : launch_reset_f64(h->cfg, mask, obs_out, st));
+    if (!mask) h->was_reset = true;
+    return BOATENV_OK;
+}
+
+static int step_common(boatenv_t h, StepArgs &a, cudaStream_t st) {
+    if (!h->was_reset) return BOATENV_ESTATE;
+    if (!a.actions || !a.obs_out || !a.reward_out || !a.done_out || a.ksteps < 1) return BOATENV_EINVAL;
+    if (!aligned16(a.obs_out)) return BOATENV_EALIGN;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(h->precision == 32 ? launch_step_f32(h->cfg, a, st) : launch_step_f64(h->cfg, a, st));
+    return BOATENV_OK;
+}
+
+int boatenv_step(boatenv_t h, const void *actions, void *obs_out, void *reward_out, uint8_t *done_out,
+                 uint8_t *term_out, void *final_obs_out, uint32_t flags, void *stream) {
+    if (!h) return BOATENV_EINVAL;
+    StepArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.env_begin = 0;
+    a.env_end = h->cfg.n_envs;
+    a.actions = actions;
+    a.action_stride = 0;
+    a.ksteps = 1;
+    a.obs_out = obs_out;
+    a.reward_out = reward_out;
+    a.done_out = done_out;
+    a.term_out = term_out;
+    a.final_obs_out = final_obs_out;
+    a.flags = flags;
+    return step_common(h, a, (cudaStream_t)stream);
+}
+
+int boatenv_step_k(boatenv_t h, const void *actions, int64_t action_stride, int32_t k, void *obs_out,
+                   void *reward_out, uint8_t *done_out, uint8_t *term_out, int32_t *steps_out, uint32_t flags,
+                   void *stream) {
+    if (!h || k < 1 || (action_stride != 0 && action_stride < h->cfg.n_envs)) return BOATENV_EINVAL;
+    StepArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.env_begin = 0;
+    a.env_end = h->cfg.n_envs;
+    a.actions = actions;
+    a.action_stride = action_stride;
+    a.ksteps = k;
+    a.obs_out = obs_out;
+    a.reward_out = reward_out;
+    a.done_out = done_out;
+    a.term_out = term_out;
+    a.steps_out = steps_out;
+    a.flags = flags;
+    return step_common(h, a, (cudaStream_t)stream);
+}
+
+static int ensure_host_path(boatenv_t h) {
+    if (h->host_path_ready) return BOATENV_OK;
+    const size_t n = (size_t)h->cfg.n_envs;
+    CUDA_TRY(cudaMalloc(&h->h_act, n * h->esize));
+    CUDA_TRY(cudaMalloc(&h->h_obs, n * kObsDim * h->esize));
+    CUDA_TRY(cudaMalloc(&h->h_rew, n * h->esize));
+    CUDA_TRY(cudaMalloc((void **)&h->h_done, n));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+    }
+    h->host_path_ready = true;
+    return BOATENV_OK;
+}
+
+int boatenv_step_host(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host, uint8_t *done_host,
+                      uint32_t flags) {
+    if (!h || !actions_host || !obs_host || !reward_host || !done_host) return BOATENV_EINVAL;
+    if (!h->was_reset) return BOATENV_ESTATE;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = ensure_host_path(h);
+    if (rc) return rc;
+    const long long n = h->cfg.n_envs;
+    // chunks are multiples of the CTA tile so that every tile keeps its 16-byte alignment
+    int nchunks = n >= 8LL * 65536 ? 8 : (n >= 4LL * 65536 ? 4 : 1);
+    long long per = ((n + nchunks - 1) / nchunks + kTile - 1) / kTile * kTile;
+    const size_t es = h->esize;
+    for (int cidx = 0; cidx < nchunks; ++cidx) {
+        const long long b = (long long)cidx * per, e = std::min(n, b + per);
+        if (b >= e) break;
+        const size_t cnt = (size_t)(e - b);
+        CUDA_TRY(cudaMemcpyAsync((char *)h->h_act + b * es, (const char *)actions_host + b * es, cnt * es,
+                                 cudaMemcpyHostToDevice, h->copy_in));
+        CUDA_TRY(cudaEventRecord(h->ev_in[cidx], h->copy_in));
+        CUDA_TRY(cudaStreamWaitEvent(h->compute, h->ev_in[cidx], 0));
+        StepArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.env_begin = b;
+        a.env_end = e;
+        a.actions = h->h_act;
+        a.ksteps = 1;
+        a.obs_out = h->h_obs;
+        a.reward_out = h->h_rew;
+        a.done_out = h->h_done;
+        a.flags = flags;
+        CUDA_TRY(h->precision == 32 ? launch_step_f32(h->cfg, a, h->compute) : launch_step_f64(h->cfg, a, h->compute));
+        CUDA_TRY(cudaEventRecord(h->ev_k[cidx], h->compute));
+        CUDA_TRY(cudaStreamWaitEvent(h->copy_out, h->ev_k[cidx], 0));
+        CUDA_TRY(cudaMemcpyAsync((char *)obs_host + b * kObsDim * es, (char *)h->h_obs + b * kObsDim * es,
+                                 cnt * kObsDim * es, cudaMemcpyDeviceToHost, h->copy_out));
+        CUDA_TRY(cudaMemcpyAsync((char *)reward_host + b * es, (char *)h->h_rew + b * es, cnt * es,
+                                 cudaMemcpyDeviceToHost, h->copy_out));
+        CUDA_TRY(cudaMemcpyAsync(done_host + b, h->h_done + b, cnt, cudaMemcpyDeviceToHost, h->copy_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->copy_out));
+    return BOATENV_OK;
+}
+
+int boatenv_get_field(boatenv_t h, int field, void *out, void *stream) {
+    if (!h || !out || field < 0 || field > BOATENV_F_EPISODE) return BOATENV_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(h->precision == 32 ? launch_get_field_f32(h->cfg, field, out, (cudaStream_t)stream)
+                                : launch_get_field_f64(h->cfg, field, out, (cudaStream_t)stream));
+    return BOATENV_OK;
+}
+
+int boatenv_set_field(boatenv_t h, int field, const void *in, void *stream) {
+    if (!h || !in || field < 0 || field > BOATENV_F_EPISODE) return BOATENV_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(h->precision == 32 ? launch_set_field_f32(h->cfg, field, in, (cudaStream_t)stream)
+                                : launch_set_field_f64(h->cfg, field, in, (cudaStream_t)stream));
+    return BOATENV_OK;
+}
+
+int boatenv_wind_length(boatenv_t h) { return h ? h->cfg.L : BOATENV_EINVAL; }
+
+int boatenv_wind_table(boatenv_t h, int64_t env_index, double *wv, double *wa, void *stream) {
+    if (!h || !wv || !wa || env_index < 0 || env_index >= h->cfg.n_envs) return BOATENV_EINVAL;
+    if (!h->was_reset) return BOATENV_ESTATE;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(launch_wind_table(h->cfg, env_index, wv, wa, (cudaStream_t)stream));
+    return BOATENV_OK;
+}
+
+int boatenv_set_episode_draws(boatenv_t h, const int32_t *s_y_start, const double *knots, void *stream) {
+    if (!h) return BOATENV_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->cfg.n_envs;
+    if (s_y_start) {
+        if (!h->ovr_s_y) CUDA_TRY(cudaMalloc((void **)&h->ovr_s_y, n * sizeof(int32_t)));
+        CUDA_TRY(cudaMemcpyAsync(h->ovr_s_y, s_y_start, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        h->cfg.ovr_s_y = h->ovr_s_y;
+    } else {
+        h->cfg.ovr_s_y = nullptr;
+    }
+    if (knots) {
+        const size_t cnt = n * 2 * (size_t)h->cfg.fp;
+        if (!h->ovr_knots) CUDA_TRY(cudaMalloc((void **)&h->ovr_knots, cnt * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(h->ovr_knots, knots, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        h->cfg.ovr_knots = h->ovr_knots;
+    } else {
+        h->cfg.ovr_knots = nullptr;
+    }
+    return BOATENV_OK;
+}
+
+int boatenv_episode_draws_host(const boatenv_params *params, uint64_t seed, int64_t global_env_id, uint32_t episode,
+                               int32_t *s_y_start_out, double *knots_out) {
+    if (!params || global_env_id < 0) return BOATENV_EINVAL;
+    DevCfg c;
+    int rc = derive_config(params, c);
+    if (rc) return rc;
+    if (s_y_start_out) *s_y_start_out = episode_s_y_start(seed, global_env_id, episode, c.s_y_half);
+    if (knots_out)
+        for (int t = 0; t < 2 * c.fp; ++t) knots_out[t] = (2 * c.fp <= 32) ? episode_knot(seed, global_env_id, episode, t) : 0.0;
+    return BOATENV_OK;
+}
+
+int boatenv_reduce_counters(boatenv_t h, double *out_device, void *stream) {
+    if (!h || !out_device) return BOATENV_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(launch_reduce_counters(h->cfg.counters, out_device, (cudaStream_t)stream));
+    return BOATENV_OK;
+}
+
+int boatenv_get_counters(boatenv_t h, double *out_host, void *stream) {
+    if (!h || !out_host) return BOATENV_EINVAL;
+    int rc = boatenv_reduce_counters(h, h->counters_out_dev, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_host, h->counters_out_dev, kNumCounters * sizeof(double), cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return BOATENV_OK;
+}
+
+int boatenv_fill_uniform_actions(boatenv_t h, uint64_t step_counter, double scale, void *actions_out, void *stream) {
+    if (!h || !actions_out) return BOATENV_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(h->precision == 32 ? launch_fill_actions_f32(h->cfg, step_counter, scale, actions_out, (cudaStream_t)stream)
+                                : launch_fill_actions_f64(h->cfg, step_counter, scale, actions_out, (cudaStream_t)stream));
+    return BOATENV_OK;
+}
+
+}  // extern "C"
+
+// accessors for the other translation units (replay.cu's fused step+store)
+namespace boatenv {
+DevCfg *handle_cfg(boatenv_t h) { return &h->cfg; }
+int handle_precision(boatenv_t h) { return h->precision; }
+int handle_device(boatenv_t h) { return h->device; }
+bool handle_was_reset(boatenv_t h) { return h->was_reset; }
+}  // namespace boatenv

@@ -1,0 +1,147 @@
+// aux_kernels.cuh -- reset, wind-table export, field access, counters, action filler.
+#pragma once
+#include "boat_step.cuh"
+
+namespace boatenv {
+
+// BoatEnv.reset()  boat_env.py:120-126 for the masked envs: a new Boat (:144-201) and a
+// new Wind (wind.py:12-18).  Each warp serves its 32 envs one at a time with the
+// cooperative wind_setup_warp().
+template <typename T>
+__global__ void __launch_bounds__(kTile) boat_reset_kernel(const __grid_constant__ DevCfg c, const uint8_t *mask,
+                                                          T *obs_out) {
+    __shared__ double scratch_s[kWarpsPerCta][kScratchDoubles];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
+    const bool active = i < c.n_envs;
+    const bool want = active && (mask == nullptr || mask[i] != 0);
+    uint32_t episode = 0;
+    if (want) episode = c.idx[i].y + 1u;
+    unsigned todo = __ballot_sync(FULL, want);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const long long e_env = __shfl_sync(FULL, i, src);
+        const uint32_t e_epi = __shfl_sync(FULL, episode, src);
+        WindSetup ws;
+        wind_setup_warp(c, e_env, e_epi, 0, scratch_s[warp], ws);
+        if (lane == src) {
+            T d[D_COUNT], wa[4], wb[4], obs[kObsDim];
+#pragma unroll
+            for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
+            const T sy0 = (c.experiment == 2) ? (T)ws.s_y_start : (T)0;  // boat_env.py:166-167
+            d[D_SY] = sy0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { wa[m] = (T)ws.a[m]; wb[m] = (T)ws.b[m]; }
+            store_group<T, D_COUNT>(c.dyn, c.n_envs, i, d);
+            c.idx[i] = make_uint2(0u, e_epi);
+            if (c.windA) store_group<T, 4>(c.windA, c.n_envs, i, wa);
+            if (c.windB) store_group<T, 4>(c.windB, c.n_envs, i, wb);
+            if (obs_out) {
+                reset_obs<T>(c, sy0, obs);
+#pragma unroll
+                for (int q = 0; q < kObsDim; ++q) obs_out[i * kObsDim + q] = obs[q];
+            }
+        }
+    }
+}
+
+// env.boat.wind.wind_velocity / wind_angle (wind.py:16-17) of one env's CURRENT episode,
+// as the step kernel sees them: per-piece folded coefficients evaluated at every sample.
+// One warp.
+static __global__ void __launch_bounds__(32) boat_wind_table_kernel(const __grid_constant__ DevCfg c, long long env,
+                                                             double *wv, double *wa) {
+    __shared__ double scratch_s[kScratchDoubles];
+    __shared__ double folded[kMaxKnots - 1][8];
+    const int lane = threadIdx.x;
+    const double PI = 3.14159265358979323846;
+    const uint32_t episode = c.idx[env].y;
+    if (c.ncurves > 0) {
+        for (int j = 0; j < c.npieces; ++j) {
+            WindSetup ws;
+            const int first_index = (j * c.Lm1 + c.npieces - 1) / c.npieces;
+            wind_setup_warp(c, env, episode, first_index, scratch_s, ws);
+            if (lane < 4) { folded[j][lane] = ws.a[lane]; folded[j][4 + lane] = ws.b[lane]; }
+        }
+    }
+    __syncwarp();
+    for (int idx = lane; idx < c.L; idx += 32) {
+        double v = 0.0, th = 0.0;
+        int j = 0, r = 0;
+        double va = 0.0, vb = 0.0;
+        if (c.ncurves > 0) {
+            piece_of(idx, c.npieces, c.Lm1, j, r);
+            const double s = (double)r * (1.0 / (double)c.Lm1);
+            const double *f = folded[j];
+            va = ((f[3] * s + f[2]) * s + f[1]) * s + f[0];
+            vb = ((f[7] * s + f[6]) * s + f[5]) * s + f[4];
+        }
+        switch (c.wind_kind) {
+        case WIND_NONE: break;
+        case WIND_CONST: v = c.p.max_velocity; th = c.direction_rad; break;
+        case WIND_VEL_CURVE: v = va; th = c.direction_rad; break;
+        case WIND_ANGLE_RECT: v = c.p.max_velocity; th = ((va <= 0.25) ? 0.0 : 1.0) * PI + PI / 2.0; break;
+        case WIND_BOTH: v = va; th = vb; break;
+        }
+        wv[idx] = v;
+        wa[idx] = th;
+    }
+}
+
+template <typename T>
+__global__ void boat_get_field_kernel(const __grid_constant__ DevCfg c, int field, void *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n_envs) return;
+    if (field < D_COUNT) {
+        constexpr int W = VecOf<T>::W;
+        const T *base = reinterpret_cast<const T *>(c.dyn);
+        reinterpret_cast<T *>(out)[i] = base[((long long)(field / W) * c.n_envs + i) * W + (field % W)];
+    } else {
+        const uint2 v = c.idx[i];
+        reinterpret_cast<uint32_t *>(out)[i] = (field == BOATENV_F_STEP_INDEX) ? v.x : v.y;
+    }
+}
+
+template <typename T>
+__global__ void boat_set_field_kernel(const __grid_constant__ DevCfg c, int field, const void *in) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n_envs) return;
+    if (field < D_COUNT) {
+        constexpr int W = VecOf<T>::W;
+        T *base = reinterpret_cast<T *>(c.dyn);
+        base[((long long)(field / W) * c.n_envs + i) * W + (field % W)] = reinterpret_cast<const T *>(in)[i];
+    } else {
+        uint2 v = c.idx[i];
+        const uint32_t x = reinterpret_cast<const uint32_t *>(in)[i];
+        if (field == BOATENV_F_STEP_INDEX) v.x = x; else v.y = x;
+        c.idx[i] = v;
+    }
+}
+
+// counters[kCounterSlots][32 doubles, first 8 used] -> out[8]
+static __global__ void boat_reduce_counters_kernel(const double *counters, double *out) {
+    const int t = threadIdx.x;
+    if (t < kNumCounters) {
+        double s = 0.0;
+        for (int r = 0; r < kCounterSlots; ++r) s += counters[r * 32 + t];
+        out[t] = s;
+    }
+}
+
+// uniform(-1,1) * scale actions from Philox(seed, global env, step_counter): the policy
+// "A1" of SURVEY.md 8(d).  24-bit values, exactly representable in fp32.
+template <typename T>
+__global__ void boat_fill_actions_kernel(const __grid_constant__ DevCfg c, unsigned long long step_counter,
+                                         double scale, T *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n_envs) return;
+    const long long g = c.env_id_offset + i;
+    const Philox4 r = philox4x32_10((uint32_t)g, (uint32_t)((unsigned long long)g >> 32), (uint32_t)step_counter,
+                                    kStreamAction | (uint32_t)((step_counter >> 32) & 0x0fffffffu), (uint32_t)c.seed,
+                                    (uint32_t)(c.seed >> 32));
+    const float u = (float)(r.x >> 8) * (1.0f / 8388608.0f) - 1.0f;
+    out[i] = (T)((float)scale * u);
+}
+
+}  // namespace boatenv

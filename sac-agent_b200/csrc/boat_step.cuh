@@ -1,0 +1,413 @@
+// boat_step.cuh -- the batched BoatEnv.step kernel (boat_env.py:67-115), one thread per
+// env, K fused sub-steps with the env state held in registers, in-kernel termination
+// cascade, statistics and auto-reset.  Instantiated for float (production) in
+// step_f32.cu and for double (validation, reference operation order, compiled with
+// -fmad=false) in step_f64.cu.
+#pragma once
+#include "common.cuh"
+#include "wind_setup.cuh"
+
+namespace boatenv {
+
+// ---------------------------------------------------------------------------------
+// fp32 transcendental helpers: Cody-Waite reduction by pi/2 + cephes-style minimax
+// polynomials on [-pi/4, pi/4]; |error| ~1e-7 for |x| up to ~1e4, no slow path.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void fast_sincosf(float x, float &s, float &c) {
+    float k = fmaf(x, 0.636619747f, 12582912.0f);
+    const int q = __float_as_int(k);
+    k -= 12582912.0f;
+    float r = fmaf(k, -1.57079637e+00f, x);   // fl32(pi/2)
+    r = fmaf(k, 4.37113883e-08f, r);          // pi/2 - fl32(pi/2) = -4.371e-8
+    const float r2 = r * r;
+    float sp = fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f);
+    sp = fmaf(sp, r2, -1.6666654611e-1f);
+    sp = fmaf(sp * r2, r, r);
+    float cp = fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f);
+    cp = fmaf(cp, r2, 4.166664568298827e-2f);
+    cp = fmaf(cp * r2, r2, fmaf(-0.5f, r2, 1.0f));
+    const float ss = (q & 1) ? cp : sp;
+    const float cc = (q & 1) ? sp : cp;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+}
+__device__ __forceinline__ float fast_sinf(float x) {
+    float s, c;
+    fast_sincosf(x, s, c);
+    return s;
+}
+
+// ---------------------------------------------------------------------------------
+// One sub-step of the dynamics.  d[] is the carried state (DynSlot order), `index` the
+// pre-increment Boat.index (== sub-steps done in this episode), (w, th) the wind sample
+// wind[index], (fwx, fwy) a precomputed wind force for the constant-wind experiments.
+// Produces the 11 normalised observations, the reward and the termination code.
+// ---------------------------------------------------------------------------------
+template <int WK>
+__device__ __forceinline__ void substep(const DevCfg &c, double (&d)[D_COUNT], int index, double action, double w,
+                                        double th, double (&obs)[kObsDim], double &reward, int &code) {
+    // fp64 validation mode: the reference's own operation order (Python's a*b*c is
+    // (a*b)*c); this translation unit is built with -fmad=false.
+    const boatenv_params &p = c.p;
+    const double PI = 3.14159265358979323846;
+    const bool first = (index == 0);  // control_blocks.py:21-22: call 0 returns initial_value
+    double rudder = d[D_RUDDER];
+    if (c.test_mode == 0) rudder += action / 10.0;  // boat_env.py:72-73
+    double v_x = d[D_VX], v_y = d[D_VY], v_r = d[D_VR];
+    const double n = 20.0;  // boat_env.py:178
+
+    double F_Wx = 0.0, F_Wy = 0.0;
+    if (WK != WIND_NONE) {  // boat_env.py:230-236, 256-262
+        const double sgn = (double)((w > 0.0) - (w < 0.0));
+        F_Wx = w * w * sgn * p.c_r_front * 0.5 * p.rho * p.boat_area_front;
+        F_Wx = F_Wx * cos(th);
+        F_Wy = w * w * sgn * p.c_r_side * 0.5 * p.rho * p.boat_area_side;
+        F_Wy = F_Wy * sin(th);
+    }
+    // eom_longitudinal  boat_env.py:213-239 (old v_x, v_y, v_r)
+    double F_R = v_x * v_x * p.c_r_front * 0.5 * p.rho * p.boat_area_front;
+    double v_x_w = v_x * (1.0 - p.wake_friction);
+    double J = v_x_w / (n * p.propeller_diameter);
+    double F_T = sin(J) * (n * n) * p.rho * c.prop_d4 * (1.0 - p.thrust_deduction);
+    double F_C = v_y * (p.boat_m + p.boat_m_y) * v_r;
+    const double a_x = (-F_R + F_T + F_C + F_Wx) / (p.boat_m + p.boat_m_x);
+    v_x = first ? 3.0 : a_x * p.dt + v_x;  // boat_env.py:158,205
+    // eom_transverse  boat_env.py:241-265 (NEW v_x, old v_y, v_r)
+    const double sin_rud = sin(rudder);
+    const double sgn_vy = (double)((v_y > 0.0) - (v_y < 0.0));
+    F_R = v_y * v_y * p.c_r_side * 0.5 * p.rho * p.boat_area_side * sgn_vy;
+    double F_RU = v_x * v_x * p.c_r_front * 0.5 * p.rho * p.rudder_area;
+    F_RU = sin_rud * F_RU;
+    F_C = v_x * (p.boat_m + p.boat_m_x) * v_r;
+    const double a_y = (-F_R + F_RU + F_C + F_Wy) / (p.boat_m + p.boat_m_y);
+    v_y = first ? 0.0 : a_y * p.dt + v_y;  // boat_env.py:163,207
+    // eom_yawning  boat_env.py:267-281 (NEW v_x, old v_r)
+    const double sgn_vr = (double)((v_r > 0.0) - (v_r < 0.0));
+    const double sgn_vx = (double)((v_x > 0.0) - (v_x < 0.0));
+    const double M_hull = v_r * v_r * p.c_r_side * 0.5 * p.rho * p.boat_area_side * p.boat_l * 5.0 * sgn_vr;
+    const double M_rudder =
+        v_x * v_x * p.c_r_side * 0.5 * p.rho * p.rudder_area * sin_rud * (p.boat_b / 2.0) * sgn_vx;
+    const double a_r = (-M_hull + M_rudder) / (p.boat_I + p.boat_Iz);
+    v_r = first ? 0.0 : a_r * p.dt + v_r;  // boat_env.py:172,209
+    // get_kinematics  boat_env.py:283-306
+    const double v = sqrt(v_x * v_x + v_y * v_y);
+    const double drift = atan2(v_x, v_y);
+    const double s_r = v_r * p.dt + d[D_SR];
+    const double dir = drift - s_r;
+    const double s_x = sin(dir) * v * p.dt + d[D_SX];
+    const double s_y = cos(dir) * v * p.dt + d[D_SY];
+    const double fuel = p.fuel - (double)(index + 1);  // boat_env.py:70
+
+    // return_state  boat_env.py:308-326
+    obs[0] = (s_x - 0.0) / (p.goal_line - 0.0);
+    obs[1] = v_x / 5.0;
+    obs[2] = a_x / 0.025;
+    obs[3] = (s_y - (-p.track_width)) / (p.track_width - (-p.track_width));
+    obs[4] = v_y / 2.0;
+    obs[5] = a_y / 0.37;
+    obs[6] = s_r / (2.0 * PI);
+    obs[7] = v_r / 8.5e-3;
+    obs[8] = a_r / 1.4e-5;
+    obs[9] = (rudder - (-PI / 3.0)) / (PI / 3.0 - (-PI / 3.0));
+    obs[10] = fuel / p.fuel;
+
+    // exponential_reward  reward_functions.py:42-57 with y_a = 0.03, y_b = 3.4 (boat_env.py:16-22)
+    const double ay = fabs(s_y);
+    double r = 0.0 - (ay / p.track_width) / (1.0 + exp((-0.03 / 3.4) * (ay - (p.track_width * 0.2))));
+    // termination cascade  boat_env.py:84-105
+    code = BOATENV_TERM_NONE;
+    if (s_x >= p.goal_line) { code = BOATENV_TERM_REACHED_GOAL; r += 1000.0; }
+    else if (ay > p.track_width + p.oob_offset || s_x < 0.0) code = BOATENV_TERM_OUT_OF_BOUNDS;
+    else if (fuel < 0.0) code = BOATENV_TERM_OUT_OF_FUEL;
+    else if (index + 1 >= c.timeout_steps) code = BOATENV_TERM_TIMEOUT;
+    else if (rudder > PI / 3.0 || rudder < -PI / 3.0) code = BOATENV_TERM_RUDDER_BROKEN;
+    if (rudder > PI / 4.0 || rudder < -PI / 4.0) r -= fabs(rudder) * 100.0;  // :107-108
+    if (fabs(s_r) > PI / 2.0) r -= 1.0;                                       // :110-111
+    reward = r;
+
+    d[D_VX] = v_x; d[D_VY] = v_y; d[D_VR] = v_r; d[D_RUDDER] = rudder;
+    d[D_SX] = s_x; d[D_SY] = s_y; d[D_SR] = s_r; d[D_RET] += r;  // :113
+}
+
+template <int WK>
+__device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], int index, float action, float w,
+                                        float th, float (&obs)[kObsDim], float &reward, int &code) {
+    // fp32 production mode: config products folded on the host (FastConsts); the
+    // sqrt/atan2/sin/cos chain of get_kinematics collapses algebraically:
+    //   sin(atan2(vx,vy) - s_r) * |v| = vx cos(s_r) - vy sin(s_r)
+    //   cos(atan2(vx,vy) - s_r) * |v| = vy cos(s_r) + vx sin(s_r)
+    const FastConsts &f = c.f;
+    const bool first = (index == 0);
+    float rudder = d[D_RUDDER];
+    if (c.test_mode == 0) rudder = fmaf(action, f.tenth, rudder);
+    float v_x = d[D_VX], v_y = d[D_VY], v_r = d[D_VR];
+
+    float F_Wx = 0.0f, F_Wy = 0.0f;
+    if (WK == WIND_CONST) { F_Wx = f.fwx_c; F_Wy = f.fwy_c; }
+    if (WK == WIND_VEL_CURVE) {
+        const float ww = w * fabsf(w);
+        F_Wx = ww * f.kwx * f.cos_dir;
+        F_Wy = ww * f.kwy * f.sin_dir;
+    }
+    if (WK == WIND_ANGLE_RECT) {  // th carries the (renormalised) rect source curve
+        const bool hi = th > 0.25f;  // wind.py:95: value <= middle/2 -> 0 else 1
+        F_Wx = hi ? f.fwx_hi : f.fwx_lo;
+        F_Wy = hi ? f.fwy_hi : f.fwy_lo;
+    }
+    if (WK == WIND_BOTH) {
+        float st, ct;
+        fast_sincosf(th, st, ct);
+        const float ww = w * fabsf(w);
+        F_Wx = ww * f.kwx * ct;
+        F_Wy = ww * f.kwy * st;
+    }
+    const float a_x = (fmaf(-f.kdx * v_x, v_x, f.kT * fast_sinf(f.kJ * v_x)) + f.cxy * v_y * v_r + F_Wx) * f.inv_mx;
+    v_x = first ? 3.0f : fmaf(a_x, f.dt, v_x);
+    const float sin_rud = fast_sinf(rudder);
+    const float a_y =
+        (fmaf(-f.kdy * v_y, fabsf(v_y), sin_rud * f.kru * v_x * v_x) + f.cyx * v_x * v_r + F_Wy) * f.inv_my;
+    v_y = first ? 0.0f : fmaf(a_y, f.dt, v_y);
+    const float a_r = fmaf(-f.kh * v_r, fabsf(v_r), f.kmr * v_x * fabsf(v_x) * sin_rud) * f.inv_I;
+    v_r = first ? 0.0f : fmaf(a_r, f.dt, v_r);
+    const float s_r = fmaf(v_r, f.dt, d[D_SR]);
+    float sr, cr;
+    fast_sincosf(s_r, sr, cr);
+    const float s_x = fmaf(fmaf(v_x, cr, -v_y * sr), f.dt, d[D_SX]);
+    const float s_y = fmaf(fmaf(v_y, cr, v_x * sr), f.dt, d[D_SY]);
+    const float fuel = f.fuel0 - (float)(index + 1);
+
+    obs[0] = s_x * f.inv_goal;
+    obs[1] = v_x * f.inv_5;
+    obs[2] = a_x * f.inv_ax;
+    obs[3] = (s_y + f.W) * f.inv_2W;
+    obs[4] = v_y * f.inv_2;
+    obs[5] = a_y * f.inv_ay;
+    obs[6] = s_r * f.inv_2pi;
+    obs[7] = v_r * f.inv_vr;
+    obs[8] = a_r * f.inv_ar;
+    obs[9] = (rudder + f.third_pi) * f.inv_rud;
+    obs[10] = fuel * f.inv_fuel;
+
+    const float ay = fabsf(s_y);
+    float r = -__fdividef(ay * f.rew_inv_W, 1.0f + __expf(f.rew_k * (ay - f.rew_y0)));
+    code = BOATENV_TERM_NONE;
+    const float ar = fabsf(rudder);
+    if (s_x >= f.goal) { code = BOATENV_TERM_REACHED_GOAL; r += 1000.0f; }
+    else if (ay > f.oob || s_x < 0.0f) code = BOATENV_TERM_OUT_OF_BOUNDS;
+    else if (fuel < 0.0f) code = BOATENV_TERM_OUT_OF_FUEL;
+    else if (index + 1 >= c.timeout_steps) code = BOATENV_TERM_TIMEOUT;
+    else if (ar > f.pi3) code = BOATENV_TERM_RUDDER_BROKEN;
+    if (ar > f.pi4) r = fmaf(-100.0f, ar, r);
+    if (fabsf(s_r) > f.pi2) r -= 1.0f;
+    reward = r;
+
+    d[D_VX] = v_x; d[D_VY] = v_y; d[D_VR] = v_r; d[D_RUDDER] = rudder;
+    d[D_SX] = s_x; d[D_SY] = s_y; d[D_SR] = s_r; d[D_RET] += r;
+}
+
+// The reset observation (boat_env.py:124 after Boat.__init__): all zeros except s_y,
+// rudder (0.5) and fuel (1).
+template <typename T>
+__device__ __forceinline__ void reset_obs(const DevCfg &c, T s_y0, T (&obs)[kObsDim]) {
+#pragma unroll
+    for (int k = 0; k < kObsDim; ++k) obs[k] = (T)0;
+    obs[3] = (T)(((double)s_y0 + c.p.track_width) / (c.p.track_width + c.p.track_width));
+    obs[9] = (T)0.5;
+    obs[10] = (T)1;
+}
+
+// Coalesced write of a CTA tile of [n][11] observations: stage in shared memory
+// (stride 11 is odd: conflict-free), then 128-bit stores of the contiguous tile.
+template <typename T>
+__device__ __forceinline__ void store_obs_tile(T *smem, T *gout, long long tile_base, int valid, const T (&obs)[kObsDim],
+                                               bool active) {
+    const int tid = threadIdx.x;
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < kObsDim; ++k) smem[tid * kObsDim + k] = obs[k];
+    }
+    __syncthreads();
+    using V = typename VecOf<T>::type;
+    constexpr int W = VecOf<T>::W;
+    const int nelem = valid * kObsDim;
+    const int nvec = nelem / W;
+    T *gbase = gout + tile_base * kObsDim;
+    V *gv = reinterpret_cast<V *>(gbase);
+    const V *sv = reinterpret_cast<const V *>(smem);
+    for (int v = tid; v < nvec; v += kTile) __stcs(gv + v, sv[v]);
+    for (int e = nvec * W + tid; e < nelem; e += kTile) gbase[e] = smem[e];
+}
+
+template <typename T, int WK>
+__global__ void __launch_bounds__(kTile, 2)
+boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
+    __shared__ __align__(16) T obs_s[kTile * kObsDim];
+    __shared__ double scratch_s[kWarpsPerCta][kScratchDoubles];
+    __shared__ double cnt_s[kNumCounters];
+
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long tile_base = a.env_begin + (long long)blockIdx.x * kTile;
+    const long long i = tile_base + tid;
+    const bool active = i < a.env_end;
+    const long long ii = active ? i : (a.env_end - 1);  // inactive lanes shadow the last env (no stores)
+    const int valid = (int)min((long long)kTile, a.env_end - tile_base);
+    if (tid < kNumCounters) cnt_s[tid] = 0.0;
+
+    // ---- load: everything issued up front (6 independent 128-bit requests per thread) ----
+    T d[D_COUNT];
+    T wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
+    load_group<T, D_COUNT>(c.dyn, c.n_envs, ii, d);
+    uint2 ix = __ldcs(c.idx + ii);
+    if (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH) load_group<T, 4>(c.windA, c.n_envs, ii, wa);
+    if (WK == WIND_BOTH) load_group<T, 4>(c.windB, c.n_envs, ii, wb);
+    const T *act = reinterpret_cast<const T *>(a.actions);
+    T action = __ldcs(act + ii);
+    __syncthreads();  // cnt_s zeroed
+
+    int index = (int)ix.x;
+    uint32_t episode = ix.y;
+    const T inv_Lm1 = (T)(1.0 / (double)c.Lm1);
+    T obs[kObsDim];
+    T rsum = (T)0;
+    int code = BOATENV_TERM_NONE, nsteps = 0;
+    bool alive = true, wind_dirty = false, did_reset = false;
+    T final_obs[kObsDim];
+
+    for (int k = 0; k < a.ksteps; ++k) {
+        if (k > 0 && a.action_stride != 0) action = __ldcs(act + (long long)k * a.action_stride + ii);
+        bool need_setup = false;
+        int index_next = 0;
+        if (alive) {
+            // ---- wind sample wind[index] from the carried piece coefficients ----
+            T w = (T)0, th = (T)0;
+            int j = 0, r = 0;
+            if (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH) {
+                piece_of(min(index, c.L - 1), c.npieces, c.Lm1, j, r);
+                const T s = (T)r * inv_Lm1;
+                const T va = ((wa[3] * s + wa[2]) * s + wa[1]) * s + wa[0];
+                if (WK == WIND_ANGLE_RECT) {
+                    if (sizeof(T) == 8) {  // wind.py:57-58,95: (value<=0.25 ? 0 : 1)*pi + pi/2
+                        w = (T)c.p.max_velocity;
+                        th = (T)(((double)va <= 0.25 ? 0.0 : 1.0) * 3.14159265358979323846 + 3.14159265358979323846 / 2.0);
+                    } else {
+                        th = va;  // the fp32 path thresholds inside substep()
+                    }
+                } else {
+                    w = va;
+                    th = (T)c.direction_rad;
+                }
+                if (WK == WIND_BOTH) th = ((wb[3] * s + wb[2]) * s + wb[1]) * s + wb[0];
+            }
+            if (WK == WIND_CONST) { w = (T)c.p.max_velocity; th = (T)c.direction_rad; }
+
+            T rew;
+            substep<WK>(c, d, index, action, w, th, obs, rew, code);
+            rsum += rew;
+            ++nsteps;
+            index += 1;
+            if (code != BOATENV_TERM_NONE) {
+                alive = false;
+                need_setup = true;  // statistics, and the reset if AUTO_RESET
+            } else if (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH) {
+                // does wind[index] (the next sub-step) live in the next spline piece?
+                if (r + c.npieces >= c.Lm1 && j + 1 <= c.npieces - 1) need_setup = true;
+            }
+            index_next = index;
+        }
+        // ---- slow path: the warp serves its lanes one at a time ----
+        unsigned pending = __ballot_sync(FULL, need_setup && active);
+        if (pending) {
+            const bool is_done = need_setup && active && code != BOATENV_TERM_NONE;
+            // statistics (info dict, boat_env.py:24-32,87-113)
+            const unsigned dmask = __ballot_sync(FULL, is_done);
+            if (dmask) {
+#pragma unroll
+                for (int t = 1; t <= 5; ++t) {
+                    const unsigned m = __ballot_sync(FULL, is_done && code == t);
+                    if (lane == 0 && m) atomicAdd(&cnt_s[t - 1], (double)__popc(m));
+                }
+                const double ret = is_done ? (double)d[D_RET] : 0.0;
+                const double s1 = warp_sum(ret), s2 = warp_sum(ret * ret);
+                if (lane == 0) {
+                    atomicAdd(&cnt_s[5], (double)__popc(dmask));
+                    atomicAdd(&cnt_s[6], s1);
+                    atomicAdd(&cnt_s[7], s2);
+                }
+            }
+            const bool auto_reset = (a.flags & BOATENV_AUTO_RESET) != 0;
+            if (is_done) {
+#pragma unroll
+                for (int q = 0; q < kObsDim; ++q) final_obs[q] = obs[q];
+            }
+            unsigned todo = __ballot_sync(FULL, need_setup && active && (!is_done || auto_reset));
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const long long e_env = __shfl_sync(FULL, i, src);
+                const int e_done = __shfl_sync(FULL, (int)is_done, src);
+                const uint32_t e_epi = __shfl_sync(FULL, episode, src) + (e_done ? 1u : 0u);
+                const int e_idx = e_done ? 0 : __shfl_sync(FULL, index_next, src);
+                WindSetup ws;
+                wind_setup_warp(c, e_env, e_epi, e_idx, scratch_s[warp], ws);
+                if (lane == src) {
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) { wa[m] = (T)ws.a[m]; wb[m] = (T)ws.b[m]; }
+                    wind_dirty = true;
+                    if (e_done) {  // Boat.__init__  boat_env.py:144-201
+#pragma unroll
+                        for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
+                        const T sy0 = (c.experiment == 2) ? (T)ws.s_y_start : (T)0;  // :166-167
+                        d[D_SY] = sy0;
+                        index = 0;
+                        episode = e_epi;
+                        did_reset = true;
+                        reset_obs<T>(c, sy0, obs);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- store ----
+    if (active) {
+        store_group<T, D_COUNT>(c.dyn, c.n_envs, i, d);
+        __stcs(c.idx + i, make_uint2((uint32_t)index, episode));
+        if (wind_dirty) {  // wind coefficients change only on the slow path
+            if (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH) store_group<T, 4>(c.windA, c.n_envs, i, wa);
+            if (WK == WIND_BOTH) store_group<T, 4>(c.windB, c.n_envs, i, wb);
+        }
+        __stcs(reinterpret_cast<T *>(a.reward_out) + i, rsum);
+        const bool done = code != BOATENV_TERM_NONE;
+        a.done_out[i] = done ? 1 : 0;
+        if (a.term_out) a.term_out[i] = (uint8_t)code;
+        if (a.steps_out) a.steps_out[i] = nsteps;
+        if (done && a.final_obs_out) {
+            T *fo = reinterpret_cast<T *>(a.final_obs_out) + i * kObsDim;
+            const T *src = did_reset ? final_obs : obs;
+#pragma unroll
+            for (int q = 0; q < kObsDim; ++q) fo[q] = src[q];
+        }
+        if (a.rp.state) {  // fused store_transition  buffer.py:13-22
+            const long long slot = (a.rp.base_cntr + i) % a.rp.mem_size;
+            const T *prev = reinterpret_cast<const T *>(a.obs_in) + i * kObsDim;
+            T *s0 = reinterpret_cast<T *>(a.rp.state) + slot * kObsDim;
+            T *s1 = reinterpret_cast<T *>(a.rp.new_state) + slot * kObsDim;
+            const T *nxt = (done && did_reset) ? final_obs : obs;
+#pragma unroll
+            for (int q = 0; q < kObsDim; ++q) { s0[q] = prev[q]; s1[q] = nxt[q]; }
+            reinterpret_cast<T *>(a.rp.action)[slot] = action;
+            reinterpret_cast<T *>(a.rp.reward)[slot] = rsum;
+            a.rp.terminal[slot] = a.rp.done_flag_mode ? (code == BOATENV_TERM_REACHED_GOAL) : done;
+        }
+    }
+    store_obs_tile<T>(obs_s, reinterpret_cast<T *>(a.obs_out), tile_base, valid, obs, active);
+
+    // ---- flush statistics: one atomic per non-zero counter per CTA, 32 replicated rows ----
+    if (tid < kNumCounters) {
+        const double v = cnt_s[tid];
+        if (v != 0.0) atomicAdd(c.counters + (blockIdx.x % kCounterSlots) * 32 + tid, v);
+    }
+}
+
+}  // namespace boatenv

@@ -1,0 +1,217 @@
+// common.cuh -- shared host/device definitions of libboatenv (sm_100a).
+//
+// State layout in HBM (DESIGN.md "data layout"): structure-of-arrays of 16-byte
+// vectors.  Scalar k of env i of a group lives in vector k / VW (VW = 16/sizeof(T)),
+// slot k % VW, at  base + (vector * n_envs + i) * 16 bytes, so that a warp's access to
+// one vector is one fully coalesced 512-byte LDG.128 / STG.128.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/boatenv.h"
+
+namespace boatenv {
+
+constexpr int kObsDim = BOATENV_OBS_DIM;
+constexpr int kTile = 256;      // envs per CTA tile == threads per CTA
+constexpr int kWarpsPerCta = kTile / 32;
+constexpr int kMaxKnots = 16;   // fixed_points supported by this build (reference default 8)
+constexpr int kCounterSlots = 32;  // replicated counter rows (spread atomics over L2 slices)
+constexpr int kNumCounters = 8;
+
+// Dynamic scalars carried per env (group "dyn"), in this order.
+enum DynSlot { D_VX = 0, D_VY = 1, D_VR = 2, D_RUDDER = 3, D_SX = 4, D_SY = 5, D_SR = 6, D_RET = 7, D_COUNT = 8 };
+
+// Wind treatment per experiment (wind.py:26-63).
+enum WindKind {
+    WIND_NONE = 0,        // exp 1, 2: zero wind
+    WIND_CONST = 1,       // exp 3: constant velocity and direction
+    WIND_VEL_CURVE = 2,   // exp 4: random velocity curve, constant direction
+    WIND_ANGLE_RECT = 3,  // exp 5: constant velocity, rectified random direction
+    WIND_BOTH = 4         // exp 6: random velocity curve and random direction curve
+};
+
+// fp32 production constants: the reference's chains of config multiplications folded
+// on the host in double precision, then rounded once.
+struct FastConsts {
+    float dt, tenth;
+    float kdx, kJ, kT, cxy, inv_mx;     // surge   boat_env.py:213-239
+    float kdy, kru, cyx, inv_my;        // sway    boat_env.py:241-265
+    float kh, kmr, inv_I;               // yaw     boat_env.py:267-281
+    float kwx, kwy;                     // wind drag factors
+    float fwx_c, fwy_c;                 // exp 3: constant wind force components
+    float cos_dir, sin_dir;             // exp 4: constant direction
+    float fwx_lo, fwy_lo, fwx_hi, fwy_hi;  // exp 5: force for angle pi/2 and 3pi/2
+    float inv_goal, inv_5, inv_ax, W, inv_2W, inv_2, inv_ay, inv_2pi, inv_vr, inv_ar,
+        third_pi, inv_rud, inv_fuel;    // obs normalisers boat_env.py:308-326
+    float fuel0, goal, oob, pi3, pi4, pi2;
+    float rew_inv_W, rew_k, rew_y0;     // reward_functions.py:52-54
+};
+
+struct DevCfg {
+    long long n_envs;
+    long long env_id_offset;
+    unsigned long long seed;
+    int experiment, wind_kind, test_mode, ncurves;
+    int fp, npieces;          // wind.fixed_points and fp - 1
+    int L, Lm1;               // wind table length int(t_max/dt) (wind.py:14-15), L - 1
+    int timeout_steps;        // first step count n with accumulated t >= t_max (boat_env.py:98)
+    int s_y_half;             // int(track_width * 0.8) (boat_env.py:148-149)
+    boatenv_params p;         // raw reference parameters (fp64 validation mode uses these)
+    double direction_rad;     // float(direction) * (pi/180)   wind.py:44
+    double prop_d4;           // np.power(propeller_diameter, 4)  boat_env.py:226
+    FastConsts f;
+    // device buffers (owned by the handle)
+    void *dyn;                // D_COUNT scalars per env, vectorised (see top of file)
+    void *windA, *windB;      // 4 cubic coefficients per env per random curve
+    uint2 *idx;               // (step index, episode index) per env
+    const double *basis;      // [npieces][4][fp] cardinal not-a-knot spline basis
+    double *counters;         // [kCounterSlots][kNumCounters]
+    const int32_t *ovr_s_y;   // optional episode-draw overrides (validation)
+    const double *ovr_knots;
+};
+
+struct ReplayView {   // fused agent.remember (main.py:83-88, buffer.py:13-22); null = off
+    void *state, *new_state, *action, *reward;
+    uint8_t *terminal;
+    long long mem_size, base_cntr;
+    int done_flag_mode;
+};
+
+struct StepArgs {
+    long long env_begin, env_end;   // this launch covers envs [env_begin, env_end)
+    const void *actions;
+    long long action_stride;   // elements between sub-step k and k+1 of one env (0: repeat)
+    int ksteps;
+    void *obs_out, *reward_out;
+    uint8_t *done_out, *term_out;
+    void *final_obs_out;
+    int32_t *steps_out;
+    const void *obs_in;        // previous observations (fused replay store only)
+    uint32_t flags;
+    ReplayView rp;
+};
+
+// ---------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter-based: no per-env RNG state in HBM.
+// ---------------------------------------------------------------------------------
+struct Philox4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
+#ifdef __CUDA_ARCH__
+    hi = __umulhi(a, b);
+    lo = a * b;
+#else
+    uint64_t p = (uint64_t)a * (uint64_t)b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+#endif
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                         uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(0xD2511F53u, c0, hi0, lo0);
+        mulhilo32(0xCD9E8D57u, c2, hi1, lo1);
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    Philox4 o = {c0, c1, c2, c3};
+    return o;
+}
+
+__host__ __device__ __forceinline__ uint32_t philox_word(const Philox4 &p, int i) {
+    return i == 0 ? p.x : (i == 1 ? p.y : (i == 2 ? p.z : p.w));
+}
+
+// Counter layout: (env_lo, env_hi, episode_or_step, stream | block).
+constexpr uint32_t kStreamEpisode = 0x00000000u;  // block 0: s_y_start; block 1+: knots
+constexpr uint32_t kStreamAction = 0xA0000000u;   // uniform(-1,1) test / bench policy
+constexpr uint32_t kStreamReplay = 0xB0000000u;   // replay-buffer sample indices
+constexpr uint32_t kStreamToy = 0xC0000000u;      // toy-env parameter jitter
+
+// np.random.sample() stand-in: 23 random bits -> (2k+1) * 2^-24, strictly inside (0,1)
+// and exactly representable in fp32 AND fp64 (both precisions see identical knots).
+__host__ __device__ __forceinline__ double knot_from_word(uint32_t w) {
+    return (double)(((w >> 9) << 1) | 1u) * (1.0 / 16777216.0);
+}
+
+// np.random.randint(-half, half) stand-in (multiply-shift range reduction).
+__host__ __device__ __forceinline__ int s_y_from_word(uint32_t w, int half) {
+    return -half + (int)(((uint64_t)w * (uint64_t)(2 * half)) >> 32);
+}
+
+__host__ __device__ __forceinline__ double episode_knot(unsigned long long seed, long long genv, uint32_t episode,
+                                                       int flat_index /* curve * fp + k */) {
+    Philox4 r = philox4x32_10((uint32_t)genv, (uint32_t)((unsigned long long)genv >> 32), episode,
+                              kStreamEpisode | (uint32_t)(1 + (flat_index >> 2)), (uint32_t)seed,
+                              (uint32_t)(seed >> 32));
+    return knot_from_word(philox_word(r, flat_index & 3));
+}
+
+__host__ __device__ __forceinline__ int episode_s_y_start(unsigned long long seed, long long genv, uint32_t episode,
+                                                         int half) {
+    Philox4 r = philox4x32_10((uint32_t)genv, (uint32_t)((unsigned long long)genv >> 32), episode, kStreamEpisode,
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    return s_y_from_word(r.x, half);
+}
+
+// ---------------------------------------------------------------------------------
+// 16-byte vector access
+// ---------------------------------------------------------------------------------
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { using type = float4; static constexpr int W = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int W = 2; };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void unpack(const float4 &v, float *o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void unpack(const double2 &v, double *o) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ float4 pack(const float *o) { return make_float4(o[0], o[1], o[2], o[3]); }
+__device__ __forceinline__ double2 pack(const double *o) { return make_double2(o[0], o[1]); }
+
+// NS scalars of env i: NS / VW streaming 128-bit loads (evict-first: every byte of
+// state is touched exactly once per step, nothing is worth keeping in L1/L2).
+template <typename T, int NS>
+__device__ __forceinline__ void load_group(const void *base, long long n, long long i, T (&out)[NS]) {
+    using V = typename VecOf<T>::type;
+    constexpr int W = VecOf<T>::W;
+    static_assert(NS % W == 0, "group must be a whole number of 16-byte vectors");
+    const V *p = reinterpret_cast<const V *>(base);
+#pragma unroll
+    for (int v = 0; v < NS / W; ++v) {
+        V x = __ldcs(p + (long long)v * n + i);
+        unpack(x, &out[v * W]);
+    }
+}
+
+template <typename T, int NS>
+__device__ __forceinline__ void store_group(void *base, long long n, long long i, const T (&in)[NS]) {
+    using V = typename VecOf<T>::type;
+    constexpr int W = VecOf<T>::W;
+    V *p = reinterpret_cast<V *>(base);
+#pragma unroll
+    for (int v = 0; v < NS / W; ++v) __stcs(p + (long long)v * n + i, pack(&in[v * W]));
+}
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif  // __CUDACC__
+
+}  // namespace boatenv

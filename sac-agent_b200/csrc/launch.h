@@ -1,0 +1,25 @@
+// launch.h -- launcher prototypes shared between the per-precision translation units
+// (step_f32.cu, step_f64.cu) and the C-ABI front end (abi.cu).
+#pragma once
+#include "common.cuh"
+
+namespace boatenv {
+
+void count_launch();
+
+cudaError_t launch_step_f32(const DevCfg &, const StepArgs &, cudaStream_t);
+cudaError_t launch_step_f64(const DevCfg &, const StepArgs &, cudaStream_t);
+cudaError_t launch_reset_f32(const DevCfg &, const uint8_t *mask, void *obs_out, cudaStream_t);
+cudaError_t launch_reset_f64(const DevCfg &, const uint8_t *mask, void *obs_out, cudaStream_t);
+cudaError_t launch_get_field_f32(const DevCfg &, int field, void *out, cudaStream_t);
+cudaError_t launch_get_field_f64(const DevCfg &, int field, void *out, cudaStream_t);
+cudaError_t launch_set_field_f32(const DevCfg &, int field, const void *in, cudaStream_t);
+cudaError_t launch_set_field_f64(const DevCfg &, int field, const void *in, cudaStream_t);
+cudaError_t launch_fill_actions_f32(const DevCfg &, unsigned long long step_counter, double scale, void *out,
+                                    cudaStream_t);
+cudaError_t launch_fill_actions_f64(const DevCfg &, unsigned long long step_counter, double scale, void *out,
+                                    cudaStream_t);
+cudaError_t launch_wind_table(const DevCfg &, long long env, double *wv, double *wa, cudaStream_t);
+cudaError_t launch_reduce_counters(const double *counters, double *out, cudaStream_t);
+
+}  // namespace boatenv
