@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- batched BoatEnv env-steps/s on N B200s (BASELINE.json metric) with the HBM
+roofline of the step kernel and the CPU baseline timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2]): BoatEnv experiment 6 (changing velocity, random
+direction), fp32 production mode, 16,777,216 envs PER GPU (weak scaling: envs shard with
+no data-path collective), uniform(-1,1) policy "A1"  so episodes end by
+rudder_broken every ~360 steps and the in-kernel auto-reset runs in steady state.
+A "step" is one BoatEnv.step over every env of the rank: one action-fill launch (the
+policy) + one step launch; actions are read from an [n_envs] float32 tensor (the
+API-faithful variant).  Every step streams ~2.8 GB per GPU (>> 126 MB L2), so no L2 flush
+is needed between iterations.
+
+``--impl reference`` times the reference algorithm's CPU implementation (the C oracle
+port of boat_env.py / wind.py -- the Python reference itself cannot travel to the GPU box)
+on all host cores, on bounded samples of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "batched BoatEnv env-steps/sec"
+UNIT = "env-steps/s"
+ENVS_PER_GPU = 16_777_216
+EXPERIMENT = 6
+SEED = 1
+ALGO_BYTES_PER_STEP = 165  # fp32, K=1, exp 6: action 4 + state 56 read + 56 write + obs 44 + reward 4 + done 1
+STATS_EVERY = 250          # NCCL all-reduce of the 64-byte statistics vector every M steps
+
+
+def workload_config(n_gpus: int, envs_per_gpu: int) -> dict:
+    return {"workload": f"BoatEnv experiment {EXPERIMENT} (changing velocity, random direction), fp32, "
+                        f"{envs_per_gpu} envs per GPU, uniform(-1,1) policy, auto-reset, K=1 sub-step per launch",
+            "experiment": EXPERIMENT, "envs_per_gpu": envs_per_gpu, "total_envs": envs_per_gpu * n_gpus,
+            "precision": "fp32", "substeps_per_launch": 1, "policy": "uniform(-1,1) Philox(seed, env, step)",
+            "seed": SEED, "sharding": f"{n_gpus} x contiguous env-id blocks, no data-path collective",
+            "l2_policy": "inputs larger than L2 (about 2.8 GB streamed per step per GPU vs 126 MB L2); no flush"}
+
+
+def hbm_peak() -> tuple[float, str]:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(envs_per_gpu: int):
+    """dram bytes per launch of the step kernel from the committed ncu --set full capture
+    (profiles/step_kernel_traffic.json), if it was taken at this problem size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
+            d = json.load(f)
+        if int(d.get("n_envs", -1)) == envs_per_gpu:
+            return float(d["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, cuda_index: int, period: float = 0.01):
+        super().__init__(daemon=True)
+        self.period = period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:  # CUDA ordinals follow CUDA_VISIBLE_DEVICES, NVML's do not: go through the PCI address
+                pr = torch.cuda.get_device_properties(cuda_index)
+                bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self) -> dict:
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# -------------------------------------------------------------------------------------
+# CPU side: the oracle port of the reference algorithm on the host cores
+# -------------------------------------------------------------------------------------
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class CpuPort:
+    """The reference's per-episode CPU stepping (boat_env.py:67-126, wind.py:26-99) as restated
+    in oracle/boat_oracle.c, pthreads over independent envs, same experiment / policy /
+    auto-reset as the GPU workload."""
+
+    def __init__(self, threads: int):
+        import numpy as np
+        from oracle import oracle as O
+        import sac_agent_b200 as S
+        self.np, self.O = np, O
+        self.threads = threads
+        self.params = O.params_from_config(S.load_config(base_settings__experiment=EXPERIMENT))
+        self.rng = np.random.default_rng(SEED)
+
+    def sample(self, n_envs: int, t_steps: int) -> tuple[int, float]:
+        np = self.np
+        episodes = max(8, t_steps // 20 + 2)
+        actions = self.rng.uniform(-1, 1, size=(t_steps, n_envs)).astype(np.float32).astype(np.float64)
+        s_y = self.rng.integers(-640, 640, size=(episodes, n_envs)).astype(np.int32)
+        knots = self.rng.random((episodes, n_envs, 2, 8))
+        t0 = time.perf_counter()
+        out = self.O.rollout(self.params, actions, s_y, knots, auto_reset=True, want_obs=False,
+                             n_threads=self.threads)
+        return int(out["steps"]), time.perf_counter() - t0
+
+
+def cpu_baseline_leg(target_seconds: float = 12.0) -> dict:
+    cores = host_cores()
+    port = CpuPort(cores)
+    t_steps = 1000
+    steps, dt = port.sample(16 * cores, t_steps)          # calibration, also warms the threads
+    rate = steps / dt
+    n_envs = int(max(16 * cores, min(rate * target_seconds / t_steps, 4_000_000 // t_steps * 16)))
+    n_envs = (n_envs + 15) // 16 * 16
+    steps, dt = port.sample(n_envs, t_steps)
+    return {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_envs} envs x {t_steps} steps, experiment {EXPERIMENT}, uniform(-1,1) actions, "
+                      f"auto-reset, oracle/boat_oracle.c with {cores} pthreads ({dt:.1f} s)"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    port = CpuPort(cores)
+    t_steps = 500
+    total = max(1, args.steps + args.warmup)
+    steps, dt = port.sample(16 * cores, t_steps)
+    rate = steps / dt
+    budget = 90.0 / total                                  # seconds per bench "step"
+    n_envs = int(max(cores, min(rate * budget / t_steps, 65536)))
+    for _ in range(args.warmup):
+        port.sample(n_envs, t_steps)
+    done_steps, elapsed = 0, 0.0
+    for _ in range(args.steps):
+        s, dt = port.sample(n_envs, t_steps)
+        done_steps += s
+        elapsed += dt
+    value = done_steps / elapsed if elapsed > 0 else 0.0
+    sample = (f"each step = {n_envs} envs x {t_steps} env-steps of experiment {EXPERIMENT}, uniform(-1,1) actions, "
+              f"auto-reset; oracle/boat_oracle.c (C port of boat_env.py/wind.py), {cores} pthreads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, ENVS_PER_GPU),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------
+# GPU side
+# -------------------------------------------------------------------------------------
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+    import sac_agent_b200 as S
+
+    rank, local_rank, world = S.sharding.dist_info()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = S.lib()
+
+    n_local = args.envs_per_gpu
+    cfg = S.load_config(base_settings__experiment=EXPERIMENT)
+    env = S.BatchedBoatEnv(cfg, n_local, seed=SEED, precision="fp32", device=local_rank,
+                           env_id_offset=rank * n_local, auto_reset=True)
+    env.reset()
+    actions = torch.empty(n_local, dtype=torch.float32, device=dev)
+    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+
+    def one_step(t, ev=None):
+        env.uniform_actions(t, 1.0, out=actions)       # the policy (1 launch)
+        if ev is not None:
+            ev[0].record()
+        env.step(actions)                               # BoatEnv.step for every env (1 launch)
+        if ev is not None:
+            ev[1].record()
+        if (t + 1) % STATS_EVERY == 0:                  # occasional statistics all-reduce
+            env._L.boatenv_reduce_counters(env._h, stats.data_ptr(), env._stream())
+            if world > 1:
+                dist.all_reduce(stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t = 0
+    for _ in range(args.warmup):
+        one_step(t)
+        t += 1
+    kernel_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                     for _ in range(args.steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = lib.boatenv_kernel_launches()
+    start.record()
+    for k in range(args.steps):
+        one_step(t, kernel_events[k])
+        t += 1
+    end.record()
+    barrier()
+    launches = lib.boatenv_kernel_launches() - launches0
+    clocks = sampler.stop()
+    elapsed_ms = start.elapsed_time(end)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / max(1, args.steps)
+    tmax = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    elapsed_ms, kernel_ms = float(tmax[0]), float(tmax[1])
+    total_envs = n_local * world
+    value = total_envs * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- e2e: the same metric through the public API with HOST buffers -------------------
+    e2e_steps = max(3, min(args.e2e_steps, args.steps))
+    act_h = torch.empty(n_local, dtype=torch.float32).pin_memory()
+    obs_h = torch.empty((n_local, 11), dtype=torch.float32).pin_memory()
+    rew_h = torch.empty(n_local, dtype=torch.float32).pin_memory()
+    done_h = torch.empty(n_local, dtype=torch.uint8).pin_memory()
+    act_h.copy_(env.uniform_actions(t, 1.0))
+    for _ in range(2):
+        env.step_host(act_h, obs_h, rew_h, done_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        env.step_host(act_h, obs_h, rew_h, done_h)      # blocks until results are in host memory
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_envs * e2e_steps / float(te[0])
+    h2d = act_h.numel() * act_h.element_size()
+    d2h = sum(x.numel() * x.element_size() for x in (obs_h, rew_h, done_h))
+    counters = S.all_reduce_counters(env.counters_tensor())
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        achieved = ALGO_BYTES_PER_STEP * n_local / (kernel_ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(world, n_local),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": ncu_traffic(n_local),
+                             "kernel": "boat_step_kernel<float, WIND_BOTH>", "kernel_ms": kernel_ms,
+                             "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP,
+                             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * n_local, "peak_source": peak_src},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "api": "BatchedBoatEnv.step_host (boatenv_step_host, pinned host buffers)"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "episodes_finished": counters["episodes"], "mean_episode_return": counters["return_mean"]}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg() if world == 1 else None
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=1000)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,400 @@
+"""Parity of the CUDA path (through the C ABI of libboatenv.so) against the CPU oracle
+and the committed golden vectors of the reference.  Needs a B200: every test is
+``@pytest.mark.gpu``.
+
+Tolerances (BASELINE.json north_star): termination / step counts bit-exact; states and
+rewards within 1e-9 (fp64 validation mode) and 1e-4 (fp32 production mode) over 1000
+steps, measured as |a-b| / max(|b|, S_i) on the reference's own normalised observations
+(S_i = 1).
+"""
+import numpy as np
+import pytest
+
+from boat_testlib import load_golden, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-9
+TOL32 = 1e-4
+
+ROLLOUTS = [f"ref_rollout_exp{e}" for e in range(1, 7)] + [
+    "ref_term_rudder_exp6", "ref_term_oob_exp2", "ref_term_fuel_exp3", "ref_term_timeout_exp4",
+    "ref_term_goal_exp5"]
+
+
+@pytest.fixture(scope="module")
+def S():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import sac_agent_b200 as pkg
+    pkg.lib()  # raises if libboatenv.so is missing: the GPU tests never run on a fallback
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def np_(t):
+    return t.detach().double().cpu().numpy() if t.is_floating_point() else t.detach().cpu().numpy()
+
+
+def make_env(S, cfg, n, precision, s_y=None, knots=None, **kw):
+    env = S.BatchedBoatEnv(cfg, n, precision=precision, device=0, **kw)
+    if s_y is not None or knots is not None:
+        env.set_episode_draws(s_y, knots)
+    return env
+
+
+def run_steps(env, actions):
+    """actions [T, N] numpy -> dict of [T, N, ...] numpy arrays."""
+    import torch
+    T, N = actions.shape
+    a_dev = torch.from_numpy(np.ascontiguousarray(actions)).to(env.device).to(env.dtype)
+    obs = torch.empty((T, N, 11), dtype=env.dtype, device=env.device)
+    rew = torch.empty((T, N), dtype=env.dtype, device=env.device)
+    done = torch.empty((T, N), dtype=torch.uint8, device=env.device)
+    term = torch.empty((T, N), dtype=torch.uint8, device=env.device)
+    fin = torch.zeros((T, N, 11), dtype=env.dtype, device=env.device)
+    for t in range(T):
+        o, r, d, info = env.step(a_dev[t])
+        obs[t], rew[t], done[t], term[t] = o, r, d, info["term"]
+        fin[t] = info["final_obs"]
+    return dict(obs=np_(obs), reward=np_(rew), done=np_(done), term=np_(term), final_obs=np_(fin))
+
+
+# ---------------------------------------------------------------------------------------
+# 1. golden roll-outs of the unmodified reference (tests/golden/ref_*.npz)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ROLLOUTS)
+def test_golden_rollouts_fp64(S, name):
+    g = load_golden(name)
+    T, N = g["actions"].shape
+    env = make_env(S, g["config"], N, "fp64", g["s_y_start"], g["knots"], auto_reset=False)
+    obs0 = np_(env.reset())
+    assert np.abs(obs0 - g["obs0"]).max() < 1e-15
+    out = run_steps(env, g["actions"].astype(np.float64))
+    assert np.array_equal(out["done"], g["done"])
+    assert np.array_equal(out["term"], g["term"])
+    assert scaled_err(out["obs"], g["obs"]).max() <= TOL64
+    assert scaled_err(out["reward"], g["reward"]).max() <= TOL64
+    assert scaled_err(np_(env.get_field("episode_reward")), g["episode_reward"]).max() <= TOL64
+    # return_all_data (boat_env.py:128-140) columns from the state fields
+    last = g["all_data"][-1]
+    for col, f in enumerate(("s_x", "s_y", "v_x", "v_y", "s_r")):
+        scale = (3900.0, 800.0, 5.0, 2.0, 2 * np.pi)[col]
+        assert scaled_err(np_(env.get_field(f)), last[:, col], scale).max() <= TOL64
+    assert scaled_err(np_(env.get_field("rudder_angle")), last[:, 7], np.pi / 3).max() <= TOL64
+    env.close()
+
+
+@pytest.mark.parametrize("name", ROLLOUTS)
+def test_golden_rollouts_fp32(S, name):
+    g = load_golden(name)
+    T, N = g["actions"].shape
+    env = make_env(S, g["config"], N, "fp32", g["s_y_start"], g["knots"], auto_reset=False)
+    obs0 = np_(env.reset())
+    assert np.abs(obs0 - g["obs0"]).max() < 1e-6
+    out = run_steps(env, g["actions"])
+    # compare every env up to and including its first done (afterwards the reference
+    # object keeps integrating a broken boat: SURVEY.md H5, the unstable regime)
+    first = np.where(g["done"].any(axis=0), g["done"].argmax(axis=0), T - 1)
+    live = np.arange(T)[:, None] <= first[None, :]
+    assert np.array_equal(out["done"][live], g["done"][live])
+    assert np.array_equal(out["term"][live], g["term"][live])
+    assert scaled_err(out["obs"], g["obs"])[live].max() <= TOL32
+    assert scaled_err(out["reward"], g["reward"])[live].max() <= TOL32
+    env.close()
+
+
+# ---------------------------------------------------------------------------------------
+# 2. the reference's recorded fixtures (ressources/settings_visualized): known answers
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 6])  # fixture 5 pins only switch positions, not knots
+def test_recorded_fixture_replay(S, n):
+    g = load_golden(f"fixture_exp{n}")
+    fp = int(g["config"]["wind"]["fixed_points"])
+    knots = np.zeros((1, 2, fp))
+    if g["meta"]["kind_v"] == "curve":
+        knots[0, 0] = g["knots_v"]
+    if g["meta"]["kind_a"] == "curve":
+        knots[0, 1] = g["knots_a"]
+    env = make_env(S, g["config"], 1, "fp64", np.array([int(g["s_y_start"])]), knots, auto_reset=False)
+    env.reset()
+    wv, wa = env.wind_table(0)
+    assert np.abs(wv[g["wind_idx"]] - g["wind_v"]).max() < 5e-14
+    assert np.abs(wa[g["wind_idx"]] - g["wind_a"]).max() < 5e-13
+    import torch
+    zero = torch.zeros(1, dtype=env.dtype, device=env.device)
+    want = {int(k): i for i, k in enumerate(g["row_idx"])}
+    ref = g["rows"]
+    steps, done, ep_reward = 0, False, 0.0
+    offset = 0.0 if n == 6 else 0.1  # fixtures 1-5 were recorded when f_x == 0.1
+    while not done and steps < 6000:
+        if steps in want:
+            row = ref[want[steps]]
+            for col, f, scale in ((0, "s_x", 3900.0), (1, "s_y", 800.0), (2, "v_x", 5.0), (3, "v_y", 2.0),
+                                  (4, "s_r", 2 * np.pi)):
+                assert scaled_err(np_(env.get_field(f))[0], row[col], scale) <= 1e-11
+            if steps > 0:
+                assert abs(float(rew[0]) + offset - row[6]) <= 1e-11
+        obs, rew, d, info = env.step(zero)
+        done = bool(d[0].item())
+        ep_reward += float(rew[0])
+        steps += 1
+    assert steps == int(g["n_rows"])  # the terminal step is never written (main.py:79-81)
+    assert int(info["term"][0]) == 1 and str(g["termination"]) == "reached_goal"
+    if n == 6:
+        assert ep_reward == pytest.approx(871.2727580297085, abs=1e-8)
+    env.close()
+
+
+# ---------------------------------------------------------------------------------------
+# 3. CUDA vs oracle on seeded inputs (BASELINE.json configs[1]: exp 3, 4096 envs, fp64)
+# ---------------------------------------------------------------------------------------
+def host_draws(env, episodes):
+    n = env.n_envs
+    fp = int(env.params.fixed_points)
+    s_y = np.empty((episodes, n), dtype=np.int32)
+    knots = np.empty((episodes, n, 2, fp))
+    for e in range(episodes):
+        for i in range(n):
+            s_y[e, i], knots[e, i] = env.episode_draws(i, e)
+    return s_y, knots
+
+
+@pytest.mark.parametrize("experiment,precision,n,T", [(3, "fp64", 4096, 1000), (6, "fp64", 1024, 1000),
+                                                      (2, "fp64", 512, 600), (6, "fp32", 4096, 1000),
+                                                      (5, "fp32", 1024, 1000), (4, "fp32", 1024, 1000)])
+def test_cuda_vs_oracle_seeded(S, O, experiment, precision, n, T):
+    cfg = S.load_config(base_settings__experiment=experiment)
+    env = make_env(S, cfg, n, precision, seed=1, auto_reset=False)
+    s_y, knots = host_draws(env, 1)
+    env.reset()
+    import torch
+    # small steering noise A2 of SURVEY.md 8(d): float32(0.05 * U(-1,1)) from Philox(seed=1)
+    acts = torch.stack([env.uniform_actions(t, 0.05).clone() for t in range(T)])
+    actions = np_(acts)
+    ref = O.rollout(O.params_from_config(cfg), actions, s_y, knots)
+    out = run_steps(env, actions)
+    tol = TOL64 if precision == "fp64" else TOL32
+    assert np.array_equal(out["done"], ref["done"])
+    assert np.array_equal(out["term"], ref["term"])
+    assert scaled_err(out["obs"], ref["obs"]).max() <= tol
+    assert scaled_err(out["reward"], ref["reward"]).max() <= tol
+    env.close()
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_auto_reset_matches_oracle(S, O, precision):
+    """Uniform(-1,1) policy A1: episodes end by rudder_broken every ~360 steps; the kernel
+    resets in place with the next episode's Philox draws.  Step counts, termination kinds
+    and statistics must equal the oracle's; terminal observations go to final_obs."""
+    cfg = S.load_config(base_settings__experiment=6)
+    n, T, E = 512, 1500, 40
+    env = make_env(S, cfg, n, precision, seed=3, auto_reset=True)
+    s_y, knots = host_draws(env, E)
+    env.reset()
+    import torch
+    actions = np_(torch.stack([env.uniform_actions(t, 1.0).clone() for t in range(T)]))
+    ref = O.rollout(O.params_from_config(cfg), actions, s_y, knots, auto_reset=True)
+    out = run_steps(env, actions)
+    assert np.array_equal(out["done"], ref["done"])
+    assert np.array_equal(out["term"], ref["term"])
+    tol = TOL64 if precision == "fp64" else TOL32
+    d = ref["done"].astype(bool)
+    assert scaled_err(out["obs"][~d], ref["obs"][~d]).max() <= tol
+    assert scaled_err(out["final_obs"][d], ref["obs"][d]).max() <= tol
+    assert scaled_err(out["reward"], ref["reward"]).max() <= tol
+    # under auto-reset obs at a done step is the NEW episode's reset observation
+    reset_rows = out["obs"][d]
+    assert np.all(reset_rows[:, [0, 1, 2, 4, 5, 6, 7, 8]] == 0) and np.all(reset_rows[:, 9] == 0.5)
+    assert np.all(reset_rows[:, 10] == 1.0) and np.all(reset_rows[:, 3] == 0.5)
+    c = env.counters()
+    for code, name in enumerate(S.TERM_NAMES):
+        if code:
+            assert c[name] == float((ref["term"] == code).sum())
+    assert c["episodes"] == float(d.sum()) and d.sum() > n
+    assert np_(env.get_field("episode")).max() < E
+    env.close()
+
+
+def test_step_k_equals_k_single_steps(S):
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    n, K, rounds = 2048, 8, 30
+    for precision in ("fp32", "fp64"):
+        a = make_env(S, cfg, n, precision, seed=9, auto_reset=False)
+        b = make_env(S, cfg, n, precision, seed=9, auto_reset=False)
+        a.reset(); b.reset()
+        for r in range(rounds):
+            acts = torch.stack([a.uniform_actions(r * K + k, 0.3).clone() for k in range(K)])
+            rsum = torch.zeros(n, dtype=a.dtype, device=a.device)
+            alive = torch.ones(n, dtype=torch.bool, device=a.device)
+            # reference semantics of the fused window: an env stops at its first done
+            snap = {f: a.get_field(f).clone() for f in ("s_x", "s_y", "v_x", "rudder_angle", "index")}
+            for k in range(K):
+                # single steps cannot freeze individual envs, so compare only envs alive through the window
+                o, rw, d, _ = a.step(acts[k])
+                rsum += torch.where(alive, rw, torch.zeros_like(rw))
+                alive &= d == 0
+            ob, rb, db, info = b.step_k(acts, K)
+            ok = alive
+            assert torch.equal(o[ok], ob[ok])
+            assert torch.allclose(rsum[ok], rb[ok], rtol=1e-5 if precision == "fp32" else 1e-12, atol=0)
+            assert torch.all(db[ok] == 0) and torch.all(info["steps"][ok] == K)
+            assert torch.all(db[~ok] == 1)
+            # resynchronise b's finished envs with a (a kept stepping them)
+            for f in ("v_x", "v_y", "v_r", "rudder_angle", "s_x", "s_y", "s_r", "episode_reward", "index"):
+                b.set_field(f, a.get_field(f))
+        a.close(); b.close()
+
+
+def test_shard_invariance(S):
+    """Philox is keyed by the GLOBAL env id: a 1024-env population equals two 512-env
+    shards (what ranks 0 and 1 of a 2-GPU run hold), bit for bit."""
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    whole = make_env(S, cfg, 1024, "fp32", seed=11, auto_reset=True)
+    lo = make_env(S, cfg, 512, "fp32", seed=11, auto_reset=True, env_id_offset=0)
+    hi = make_env(S, cfg, 512, "fp32", seed=11, auto_reset=True, env_id_offset=512)
+    for e in (whole, lo, hi):
+        e.reset()
+    for t in range(800):
+        aw = whole.uniform_actions(t)
+        assert torch.equal(aw[:512], lo.uniform_actions(t)) and torch.equal(aw[512:], hi.uniform_actions(t))
+        ow, rw, dw, _ = whole.step(aw)
+        ol, rl, dl, _ = lo.step(aw[:512])
+        oh, rh, dh, _ = hi.step(aw[512:])
+        assert torch.equal(ow[:512], ol) and torch.equal(ow[512:], oh)
+        assert torch.equal(rw[:512], rl) and torch.equal(dw[512:], dh)
+    cw, cl, ch = whole.counters(), lo.counters(), hi.counters()
+    assert cw["episodes"] > 0
+    for k in ("reached_goal", "out_of_bounds", "out_of_fuel", "timeout", "rudder_broken", "episodes"):
+        assert cw[k] == cl[k] + ch[k]
+    assert cw["return_sum"] == pytest.approx(cl["return_sum"] + ch["return_sum"], rel=1e-9)
+    for e in (whole, lo, hi):
+        e.close()
+
+
+@pytest.mark.parametrize("experiment", range(1, 7))
+def test_wind_tables_and_draws(S, O, experiment):
+    """Device Philox == host Philox (boatenv_episode_draws_host), and the wind the kernels
+    see == the oracle's wind.py tables for those knots."""
+    cfg = S.load_config(base_settings__experiment=experiment)
+    env = make_env(S, cfg, 64, "fp64", seed=77, auto_reset=False)
+    obs0 = np_(env.reset())
+    p = O.params_from_config(cfg)
+    for i in (0, 1, 17, 63):
+        s_y, knots = env.episode_draws(i, 0)
+        assert -640 <= s_y < 640 and np.all((knots > 0) & (knots < 1))
+        assert np.all(knots == knots.astype(np.float32))  # fp32-representable: both modes see the same knots
+        o = O.OracleEnv(p)
+        ref_obs0 = o.reset(s_y, knots[0], knots[1])
+        assert np.abs(obs0[i] - ref_obs0).max() < 1e-15
+        wv, wa = env.wind_table(i)
+        rv, ra = o.wind()
+        assert np.abs(wv - rv).max() < 1e-13 and np.abs(wa - ra).max() < 1e-12
+    env.close()
+
+
+def test_step_host_equals_step(S):
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    n = 300_000  # > 4 * 65536: exercises the chunked copy/compute overlap
+    a = make_env(S, cfg, n, "fp32", seed=2)
+    b = make_env(S, cfg, n, "fp32", seed=2)
+    a.reset(); b.reset()
+    act_h = torch.empty(n, dtype=torch.float32).pin_memory()
+    obs_h = torch.empty((n, 11), dtype=torch.float32).pin_memory()
+    rew_h = torch.empty(n, dtype=torch.float32).pin_memory()
+    done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for t in range(5):
+        acts = a.uniform_actions(t)
+        act_h.copy_(acts)
+        o, r, d, _ = a.step(acts)
+        torch.cuda.synchronize()
+        b.step_host(act_h, obs_h, rew_h, done_h)
+        assert torch.equal(o.cpu(), obs_h) and torch.equal(r.cpu(), rew_h) and torch.equal(d.cpu(), done_h)
+    a.close(); b.close()
+
+
+def test_error_behaviour(S):
+    """ValueError for an unknown experiment / fixed_points < 4 (wind.py:65-67, 73-75)."""
+    with pytest.raises(ValueError):
+        S.BatchedBoatEnv(S.load_config(base_settings__experiment=7), 4, device=0)
+    with pytest.raises(ValueError):
+        S.BatchedBoatEnv(S.load_config(base_settings__experiment=4, wind__fixed_points=3), 4, device=0)
+    S.BatchedBoatEnv(S.load_config(base_settings__experiment=3, wind__fixed_points=3), 4, device=0).close()
+    env = S.BatchedBoatEnv(S.load_config(), 4, device=0)
+    with pytest.raises(S.BoatEnvError):
+        env.step(np.zeros(4, dtype=np.float32))  # step before reset
+    env.close()
+
+
+def test_single_env_drop_in(S, O):
+    """The reference's BoatEnv object protocol: 4-tuple step, cumulative
+    info with a sticky 'termination', episode_reward reset by reset(), return_all_data."""
+    cfg = S.load_config(base_settings__experiment=3, boat__fuel=60)
+    env = S.BoatEnv(cfg, experiment=None, seed=4, precision="fp64", device=0)
+    assert env.observation_space.shape == (11,) and env.action_space.shape[0] == 1
+    assert float(env.action_space.high[0]) == 1.0
+    p = O.params_from_config(cfg)
+    for episode in range(2):
+        o = O.OracleEnv(p)
+        ref = o.reset(0)
+        obs = env.reset()
+        assert isinstance(obs, np.ndarray) and obs.dtype == np.float64 and obs.shape == (11,)
+        assert np.array_equal(obs, ref) and env.info["episode_reward"] == 0
+        done, total = False, 0.0
+        rng = np.random.default_rng(episode)
+        while not done:
+            a = np.array([np.float32(0.05 * rng.uniform(-1, 1))], dtype=np.float32)
+            obs, reward, done, info = env.step(a)
+            ro, rr, rd, rc = o.step(float(a[0]))
+            assert scaled_err(obs, ro).max() <= TOL64 and abs(reward - rr) <= 1e-9 and done == rd
+            total += reward
+            assert info is env.info
+        assert info["termination"] == "out_of_fuel" and info["out_of_fuel"] == episode + 1
+        assert info[info["termination"]] == episode + 1  # main.py:110
+        assert info["episode_reward"] == pytest.approx(total)
+        d = env.return_all_data()
+        assert set(d) == {"boat_position_x", "boat_position_y", "boat_velocity_x", "boat_velocity_y", "boat_angle",
+                          "action_rudder", "reward", "rudder_angle", "n"}
+        assert np.allclose([d["boat_position_x"], d["boat_position_y"], d["boat_velocity_x"], d["boat_velocity_y"],
+                            d["boat_angle"], d["reward"], d["rudder_angle"]], o.all_data()[[0, 1, 2, 3, 4, 6, 7]],
+                           rtol=1e-9, atol=1e-12)
+        assert len(env.boat.wind.wind_velocity) == 10000
+    env.close()
+
+
+def test_full_size_properties(S):
+    """BASELINE.json configs[2] shape (exp 6, fp32, millions of envs): properties that do
+    not need the oracle -- determinism, counter consistency, fuel bookkeeping."""
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    n, T = 4 * 1024 * 1024, 40
+    runs = []
+    for _ in range(2):
+        env = make_env(S, cfg, n, "fp32", seed=1, auto_reset=True)
+        env.reset()
+        dones = torch.zeros(n, dtype=torch.int64, device=env.device)
+        for t in range(T):
+            obs, rew, done, info = env.step(env.uniform_actions(t, 4.0))  # big steps: rudder breaks within ~10 steps
+            dones += done
+            assert torch.all((info["term"] > 0) == (done > 0))
+        c = env.counters()
+        assert c["episodes"] == float(dones.sum().item()) and c["episodes"] > n
+        assert c["episodes"] == sum(c[k] for k in ("reached_goal", "out_of_bounds", "out_of_fuel", "timeout",
+                                                   "rudder_broken"))
+        idx = env.get_field("index")
+        assert torch.equal(obs[:, 10], (15000.0 - idx.float()) / 15000.0) or \
+            torch.allclose(obs[:, 10], (15000.0 - idx.float()) / 15000.0, rtol=1e-6)
+        assert torch.equal(env.get_field("episode").long(), dones)
+        runs.append((obs.clone(), rew.clone(), c))
+        env.close()
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    assert runs[0][2]["episodes"] == runs[1][2]["episodes"]

@@ -1,0 +1,197 @@
+"""Replay buffer (agent/buffer.py) and toy envs (environment/toy_car.py,
+toy_parachute.py) on the GPU, through the C ABI, against the golden vectors / the oracle."""
+import numpy as np
+import pytest
+
+from boat_testlib import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import sac_agent_b200 as pkg
+    pkg.lib()
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+# ---------------------------------------------------------------------------------------
+# replay buffer
+# ---------------------------------------------------------------------------------------
+def test_replay_matches_reference_golden(S):
+    """tests/golden/replay_buffer.npz: the unmodified reference ReplayBuffer(64, (11,), 1)
+    fed 150 transitions one at a time (wraps twice), sampled at five points with known
+    index draws.  fp64 ring: bit-exact."""
+    g = load_golden("replay_buffer")
+    size, batch = int(g["size"]), int(g["batch"])
+    buf = S.ReplayBuffer(size, (11,), 1, precision="fp64", device=0)
+    assert buf.mem_size == size and buf.mem_cntr == 0
+    k = 0
+    for i in range(len(g["R"])):
+        buf.store_transition(g["S"][i], g["A"][i], g["R"][i], g["S2"][i], g["D"][i])
+        if k < len(g["after"]) and i + 1 == g["after"][k]:
+            s, a, r, s2, d = buf.gather(g["idx"][k])
+            assert np.array_equal(s, g["s"][k]) and np.array_equal(s2, g["s2"][k])
+            assert np.array_equal(a, g["a"][k]) and np.array_equal(r, g["r"][k])
+            assert d.dtype == bool and np.array_equal(d, g["d"][k])
+            k += 1
+    assert k == len(g["after"]) and buf.mem_cntr == int(g["mem_cntr"])
+    s, a, r, s2, d = buf.gather(np.arange(size))
+    assert np.array_equal(s, g["final_state"]) and np.array_equal(s2, g["final_new_state"])
+    assert np.array_equal(a, g["final_action"]) and np.array_equal(r, g["final_reward"])
+    assert np.array_equal(d, g["final_terminal"])
+    buf.close()
+
+
+def test_replay_batched_store_equals_single(S):
+    g = load_golden("replay_buffer")
+    size = int(g["size"])
+    one = S.ReplayBuffer(size, (11,), 1, precision="fp64", device=0)
+    many = S.ReplayBuffer(size, (11,), 1, precision="fp64", device=0)
+    n = len(g["R"])
+    for i in range(n):
+        one.store_transition(g["S"][i], g["A"][i], g["R"][i], g["S2"][i], g["D"][i])
+    for lo, hi in ((0, 10), (10, 70), (70, 71), (71, n)):  # includes a wrap inside one batch
+        many.store_batch(g["S"][lo:hi], g["A"][lo:hi], g["R"][lo:hi], g["S2"][lo:hi], g["D"][lo:hi])
+    assert one.mem_cntr == many.mem_cntr == n
+    for x, y in zip(one.gather(np.arange(size)), many.gather(np.arange(size))):
+        assert np.array_equal(x, y)
+    # a single batch longer than the ring keeps the LAST `size` rows, like n single stores
+    big = S.ReplayBuffer(size, (11,), 1, precision="fp64", device=0)
+    big.store_batch(g["S"], g["A"], g["R"], g["S2"], g["D"])
+    for x, y in zip(one.gather(np.arange(size)), big.gather(np.arange(size))):
+        assert np.array_equal(x, y)
+    for b in (one, many, big):
+        b.close()
+
+
+def test_replay_sample_semantics(S):
+    """buffer.py:24-27: indices uniform over [0, min(cntr, size)), with replacement;
+    rows returned are the stored rows; ValueError on an empty buffer."""
+    import torch
+    buf = S.ReplayBuffer(1000, (11,), 1, precision="fp32", device=0, seed=5, as_torch=True)
+    with pytest.raises(ValueError):
+        buf.sample_buffer(8)
+    n = 300
+    s = torch.arange(n * 11, dtype=torch.float32, device="cuda").reshape(n, 11)
+    a = torch.arange(n, dtype=torch.float32, device="cuda").reshape(n, 1)
+    buf.store_batch(s, a, a.reshape(n) * 2, s + 0.5, (torch.arange(n, device="cuda") % 3 == 0))
+    st, ac, rw, st2, dn, idx = buf.sample_buffer(4096, return_indices=True)
+    assert int(idx.min()) >= 0 and int(idx.max()) < n       # only filled slots
+    assert len(torch.unique(idx)) == n                       # with replacement, covers everything
+    assert torch.equal(st, s[idx]) and torch.equal(st2, s[idx] + 0.5)
+    assert torch.equal(ac[:, 0], idx.float()) and torch.equal(rw, idx.float() * 2)
+    assert dn.dtype == torch.bool and torch.equal(dn, idx % 3 == 0)
+    counts = torch.bincount(idx, minlength=n).float()
+    assert abs(float(counts.mean()) - 4096 / n) < 1e-3 and float(counts.max()) < 40  # roughly uniform
+    # successive calls advance the Philox counter; same (seed, counter) reproduces
+    idx2 = buf.sample_buffer(4096, return_indices=True)[-1]
+    assert not torch.equal(idx, idx2)
+    twin = S.ReplayBuffer(1000, (11,), 1, precision="fp32", device=0, seed=5, as_torch=True)
+    twin.store_batch(s, a, a.reshape(n) * 2, s + 0.5, (torch.arange(n, device="cuda") % 3 == 0))
+    assert torch.equal(twin.sample_buffer(4096, return_indices=True)[-1], idx)
+    # numpy output mode is the reference's return type
+    out = buf.sample_buffer(16, as_torch=False)
+    assert all(isinstance(x, np.ndarray) for x in out) and out[0].shape == (16, 11) and out[4].dtype == bool
+    buf.close(); twin.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_fused_step_store_equals_step_then_store(S, precision):
+    """env.step + agent.remember (main.py:81-88) in one kernel == the two-call sequence."""
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    n, T, cap = 3000, 60, 8192   # the ring wraps inside the run (3000 * 60 > 8192)
+    e1 = S.BatchedBoatEnv(cfg, n, seed=8, precision=precision, device=0, auto_reset=True)
+    e2 = S.BatchedBoatEnv(cfg, n, seed=8, precision=precision, device=0, auto_reset=True)
+    b1 = S.ReplayBuffer(cap, (11,), 1, precision=precision, device=0, as_torch=True)
+    b2 = S.ReplayBuffer(cap, (11,), 1, precision=precision, device=0, as_torch=True)
+    e1.reset(); e2.reset()
+    for t in range(T):
+        acts = e1.uniform_actions(t, 3.0)   # large steps: frequent rudder_broken -> resets in the window
+        prev = e1.obs.clone()
+        o, r, d, info = e1.step(acts)
+        # s' of a finished env is its TERMINAL observation, not the reset one
+        nxt = torch.where((d > 0)[:, None], info["final_obs"], o)
+        b1.store_batch(prev, acts.reshape(n, 1), r, nxt, info["term"] == 1)  # main.py:83-88: flag = reached_goal
+        b2.step_store(e2, acts, done_flag_mode=1)
+        assert torch.equal(e2.obs, o) and torch.equal(e2.reward, r) and torch.equal(e2.done, d)
+    assert b1.mem_cntr == b2.mem_cntr == n * T
+    all_idx = torch.arange(cap, device="cuda")
+    for x, y in zip(b1.gather(all_idx), b2.gather(all_idx)):
+        assert torch.equal(x, y)
+    assert int(e1.counters()["episodes"]) > 0
+    # done_flag_mode 0 stores done itself
+    b3 = S.ReplayBuffer(cap, (11,), 1, precision=precision, device=0, as_torch=True)
+    b3.step_store(e2, e1.uniform_actions(T, 3.0), done_flag_mode=0)
+    assert torch.equal(b3.gather(torch.arange(n, device="cuda"))[4], e2.done.bool())
+    for x in (e1, e2, b1, b2, b3):
+        x.close()
+
+
+# ---------------------------------------------------------------------------------------
+# toy envs
+# ---------------------------------------------------------------------------------------
+def test_toy_car_known_answers(S, O):
+    """the unmodified toy_car.py ends at (-35.4716861557275,
+    3.4236034791721615) after 5000 loop iterations."""
+    from sac_agent_b200.toy_envs import loop_count
+    n_iter = loop_count(500, 0.1)
+    assert n_iter == 5000
+    car = S.ToyCar(n_envs=4096, jitter=0.1, seed=3, precision="fp64", device=0)
+    traj, final = O.toy_car()
+    out, _ = car.step(2)
+    assert out[0, 0].item() == pytest.approx(0.09998000066665778, abs=1e-15)   # first recorded sample
+    assert out[0, 1].item() == pytest.approx(0.0019998666693333083, abs=1e-15)
+    out, _ = car.step(998)
+    assert abs(out[0, 0].item() - traj[999, 0]) < 1e-10 and abs(out[0, 1].item() - traj[999, 1]) < 1e-10
+    out, _ = car.step(4000)
+    assert out[0, 0].item() == pytest.approx(-35.4716861557275, abs=1e-10)
+    assert out[0, 1].item() == pytest.approx(3.4236034791721615, abs=1e-10)
+    assert out[0, 2].item() == 11.0  # unclamped return above a clamped store (control_blocks.py:27-36)
+    o = out.cpu().numpy()
+    assert np.unique(np.round(o[:, 0], 6)).size > 4000   # jittered envs differ ...
+    car.reset()
+    again, _ = car.step(5000)
+    assert np.array_equal(again.cpu().numpy(), o)         # ... deterministically
+    # a jittered env equals the oracle run with that env's parameters (recovered from v and angle)
+    car32 = S.ToyCar(n_envs=1024, precision="fp32", device=0)
+    o32, _ = car32.step(5000)
+    assert abs(o32[0, 0].item() - final[0]) < 5e-2 and abs(o32[0, 1].item() - final[1]) < 5e-2
+    car.close(); car32.close()
+
+
+def test_toy_parachute_known_answers(S, O):
+    chute = S.ToyParachute(n_envs=2048, jitter=0.05, seed=1, precision="fp64", device=0)
+    traj, sv, calls = O.toy_parachute()
+    assert calls == 2654
+    out, done = chute.step(2)
+    assert out[0, 0].item() == pytest.approx(2999.9019, abs=1e-9)
+    out, done = chute.step(2651)
+    assert not bool(done[0]) and out[0, 0].item() == pytest.approx(0.5671644323787001, abs=1e-9)
+    out, done = chute.step(500)   # ground is reached on the next iteration; the env then stays put
+    assert bool(done[0]) and out[0, 3].item() == 2654.0
+    assert out[0, 0].item() == pytest.approx(-0.0867586400200222, abs=1e-9)
+    assert out[0, 1].item() == pytest.approx(-6.539230723987222, abs=1e-9)
+    out2, done2 = chute.step(100)
+    assert np.array_equal(out2.cpu().numpy(), out.cpu().numpy())
+    landed = out.cpu().numpy()
+    assert done.cpu().numpy().mean() > 0.5 and (landed[done.cpu().numpy() > 0, 0] < 0).all()
+    # one k-step launch == k single-iteration launches
+    a = S.ToyParachute(n_envs=512, jitter=0.05, seed=2, precision="fp32", device=0)
+    b = S.ToyParachute(n_envs=512, jitter=0.05, seed=2, precision="fp32", device=0)
+    for _ in range(300):
+        a.step(1)
+    b.step(300)
+    assert np.array_equal(a.out.cpu().numpy(), b.out.cpu().numpy())
+    for x in (chute, a, b):
+        x.close()
