@@ -281,6 +281,16 @@ def run_ours(args) -> None:
     value = total_envs * args.steps / (elapsed_ms * 1e-3)
 
     # ---- e2e: the same metric through the public API with HOST buffers -------------------
+    if args.no_e2e:  # profiling runs (ncu): the device-timed part only
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "kernel_ms": kernel_ms,
+                              "gpu_launches": int(launches), "clocks": clocks, "note": "--no-e2e profiling run"}),
+                  flush=True)
+        env.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     e2e_steps = max(3, min(args.e2e_steps, args.steps))
     act_h = torch.empty(n_local, dtype=torch.float32).pin_memory()
     obs_h = torch.empty((n_local, 11), dtype=torch.float32).pin_memory()
@@ -337,6 +347,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="device-timed part only (for ncu runs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps
