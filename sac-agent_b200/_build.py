@@ -52,7 +52,8 @@ def _compile(unit: str, flags, verbose: bool) -> str:
     obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
     if os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), _deps_mtime()):
         return obj
-    cmd = [nvcc(), *ARCH, *COMMON, *flags, "-c", src, "-o", obj]
+    extra = os.environ.get("BOATENV_NVCC_FLAGS", "").split()  # tuning experiments only
+    cmd = [nvcc(), *ARCH, *COMMON, *flags, *extra, "-c", src, "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

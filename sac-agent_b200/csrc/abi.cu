@@ -122,8 +122,23 @@ static int derive_config(const boatenv_params *p, DevCfg &c) {
     c.npieces = c.fp - 1;
     const double Ld = p->t_max / p->dt;  // wind.py:14-15
     if (!(Ld >= 2.0) || Ld > 16777216.0) return BOATENV_EUNSUPPORTED;
+    if (Ld < 4.0) return BOATENV_EUNSUPPORTED;
     c.L = (int)Ld;
     c.Lm1 = c.L - 1;
+    c.inv_Lm1 = 1.0 / (double)c.Lm1;
+    {   // exact floor(n / Lm1) for 0 <= n <= L * npieces as a multiply-high (Granlund & Montgomery):
+        // p = max(32, N + l) with 2^N > n_max, 2^l >= Lm1;  m = ceil(2^p / Lm1) < 2^32
+        const unsigned long long nmax = (unsigned long long)c.L * (unsigned long long)c.npieces;
+        int N = 1, l = 0;
+        while ((1ULL << N) <= nmax) ++N;
+        while ((1ULL << l) < (unsigned long long)c.Lm1) ++l;
+        int pw = N + l < 32 ? 32 : N + l;
+        const unsigned __int128 two_p = (unsigned __int128)1 << pw;
+        const unsigned __int128 m = (two_p + (unsigned)c.Lm1 - 1) / (unsigned)c.Lm1;
+        if (m >> 32) return BOATENV_EUNSUPPORTED;
+        c.magic_m = (unsigned)m;
+        c.magic_s = (unsigned)(pw - 32);
+    }
     {   // boat_env.py:69,98: t accumulates dt; timeout at the first step with t_max <= t
         double t = 0.0;
         int n = 0;
@@ -187,6 +202,7 @@ static int derive_config(const boatenv_params *p, DevCfg &c) {
     f.rew_inv_W = (float)(1.0 / p->track_width);
     f.rew_k = (float)(-0.03 / 3.4);
     f.rew_y0 = (float)(p->track_width * 0.2);
+    f.inv_Lm1 = (float)c.inv_Lm1;
     return BOATENV_OK;
 }
 

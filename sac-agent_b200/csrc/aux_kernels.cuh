@@ -24,26 +24,29 @@ __global__ void __launch_bounds__(kTile) boat_reset_kernel(const __grid_constant
         todo &= todo - 1;
         const long long e_env = __shfl_sync(FULL, i, src);
         const uint32_t e_epi = __shfl_sync(FULL, episode, src);
-        WindSetup ws;
-        wind_setup_warp(c, e_env, e_epi, 0, scratch_s[warp], ws);
+        if (c.ncurves > 0) wind_setup_warp(c, e_env, e_epi, 0, scratch_s[warp]);
         if (lane == src) {
             T d[D_COUNT], wa[4], wb[4], obs[kObsDim];
 #pragma unroll
             for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
-            const T sy0 = (c.experiment == 2) ? (T)ws.s_y_start : (T)0;  // boat_env.py:166-167
+            const T sy0 = (T)episode_start_y(c, i, e_epi);  // boat_env.py:166-167
             d[D_SY] = sy0;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) { wa[m] = (T)ws.a[m]; wb[m] = (T)ws.b[m]; }
+            for (int m = 0; m < 4; ++m) {
+                wa[m] = c.ncurves > 0 ? (T)scratch_s[warp][kCoefDoubles + m] : (T)0;
+                wb[m] = c.ncurves > 0 ? (T)scratch_s[warp][kCoefDoubles + 4 + m] : (T)0;
+            }
             store_group<T, D_COUNT>(c.dyn, c.n_envs, i, d);
             c.idx[i] = make_uint2(0u, e_epi);
             if (c.windA) store_group<T, 4>(c.windA, c.n_envs, i, wa);
             if (c.windB) store_group<T, 4>(c.windB, c.n_envs, i, wb);
             if (obs_out) {
-                reset_obs<T>(c, sy0, obs);
+                stage_reset_obs<T>(c, obs, sy0);
 #pragma unroll
                 for (int q = 0; q < kObsDim; ++q) obs_out[i * kObsDim + q] = obs[q];
             }
         }
+        __syncwarp();
     }
 }
 
@@ -59,10 +62,10 @@ static __global__ void __launch_bounds__(32) boat_wind_table_kernel(const __grid
     const uint32_t episode = c.idx[env].y;
     if (c.ncurves > 0) {
         for (int j = 0; j < c.npieces; ++j) {
-            WindSetup ws;
             const int first_index = (j * c.Lm1 + c.npieces - 1) / c.npieces;
-            wind_setup_warp(c, env, episode, first_index, scratch_s, ws);
-            if (lane < 4) { folded[j][lane] = ws.a[lane]; folded[j][4 + lane] = ws.b[lane]; }
+            wind_setup_warp(c, env, episode, first_index, scratch_s);
+            if (lane < 8) folded[j][lane] = scratch_s[kCoefDoubles + lane];
+            __syncwarp();
         }
     }
     __syncwarp();
@@ -71,8 +74,8 @@ static __global__ void __launch_bounds__(32) boat_wind_table_kernel(const __grid
         int j = 0, r = 0;
         double va = 0.0, vb = 0.0;
         if (c.ncurves > 0) {
-            piece_of(idx, c.npieces, c.Lm1, j, r);
-            const double s = (double)r * (1.0 / (double)c.Lm1);
+            piece_of(c, idx, j, r);
+            const double s = (double)r * c.inv_Lm1;
             const double *f = folded[j];
             va = ((f[3] * s + f[2]) * s + f[1]) * s + f[0];
             vb = ((f[7] * s + f[6]) * s + f[5]) * s + f[4];

@@ -40,12 +40,12 @@ __device__ __forceinline__ float fast_sinf(float x) {
 // ---------------------------------------------------------------------------------
 // One sub-step of the dynamics.  d[] is the carried state (DynSlot order), `index` the
 // pre-increment Boat.index (== sub-steps done in this episode), (w, th) the wind sample
-// wind[index], (fwx, fwy) a precomputed wind force for the constant-wind experiments.
-// Produces the 11 normalised observations, the reward and the termination code.
+// wind[index].  Updates d[], returns the three accelerations (they are observations),
+// the reward and the termination code.
 // ---------------------------------------------------------------------------------
 template <int WK>
 __device__ __forceinline__ void substep(const DevCfg &c, double (&d)[D_COUNT], int index, double action, double w,
-                                        double th, double (&obs)[kObsDim], double &reward, int &code) {
+                                        double th, double (&acc)[3], double &reward, int &code) {
     // fp64 validation mode: the reference's own operation order (Python's a*b*c is
     // (a*b)*c); this translation unit is built with -fmad=false.
     const boatenv_params &p = c.p;
@@ -98,19 +98,6 @@ __device__ __forceinline__ void substep(const DevCfg &c, double (&d)[D_COUNT], i
     const double s_y = cos(dir) * v * p.dt + d[D_SY];
     const double fuel = p.fuel - (double)(index + 1);  // boat_env.py:70
 
-    // return_state  boat_env.py:308-326
-    obs[0] = (s_x - 0.0) / (p.goal_line - 0.0);
-    obs[1] = v_x / 5.0;
-    obs[2] = a_x / 0.025;
-    obs[3] = (s_y - (-p.track_width)) / (p.track_width - (-p.track_width));
-    obs[4] = v_y / 2.0;
-    obs[5] = a_y / 0.37;
-    obs[6] = s_r / (2.0 * PI);
-    obs[7] = v_r / 8.5e-3;
-    obs[8] = a_r / 1.4e-5;
-    obs[9] = (rudder - (-PI / 3.0)) / (PI / 3.0 - (-PI / 3.0));
-    obs[10] = fuel / p.fuel;
-
     // exponential_reward  reward_functions.py:42-57 with y_a = 0.03, y_b = 3.4 (boat_env.py:16-22)
     const double ay = fabs(s_y);
     double r = 0.0 - (ay / p.track_width) / (1.0 + exp((-0.03 / 3.4) * (ay - (p.track_width * 0.2))));
@@ -125,13 +112,14 @@ __device__ __forceinline__ void substep(const DevCfg &c, double (&d)[D_COUNT], i
     if (fabs(s_r) > PI / 2.0) r -= 1.0;                                       // :110-111
     reward = r;
 
+    acc[0] = a_x; acc[1] = a_y; acc[2] = a_r;
     d[D_VX] = v_x; d[D_VY] = v_y; d[D_VR] = v_r; d[D_RUDDER] = rudder;
     d[D_SX] = s_x; d[D_SY] = s_y; d[D_SR] = s_r; d[D_RET] += r;  // :113
 }
 
 template <int WK>
 __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], int index, float action, float w,
-                                        float th, float (&obs)[kObsDim], float &reward, int &code) {
+                                        float th, float (&acc)[3], float &reward, int &code) {
     // fp32 production mode: config products folded on the host (FastConsts); the
     // sqrt/atan2/sin/cos chain of get_kinematics collapses algebraically:
     //   sin(atan2(vx,vy) - s_r) * |v| = vx cos(s_r) - vy sin(s_r)
@@ -176,18 +164,6 @@ __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], in
     const float s_y = fmaf(fmaf(v_y, cr, v_x * sr), f.dt, d[D_SY]);
     const float fuel = f.fuel0 - (float)(index + 1);
 
-    obs[0] = s_x * f.inv_goal;
-    obs[1] = v_x * f.inv_5;
-    obs[2] = a_x * f.inv_ax;
-    obs[3] = (s_y + f.W) * f.inv_2W;
-    obs[4] = v_y * f.inv_2;
-    obs[5] = a_y * f.inv_ay;
-    obs[6] = s_r * f.inv_2pi;
-    obs[7] = v_r * f.inv_vr;
-    obs[8] = a_r * f.inv_ar;
-    obs[9] = (rudder + f.third_pi) * f.inv_rud;
-    obs[10] = fuel * f.inv_fuel;
-
     const float ay = fabsf(s_y);
     float r = -__fdividef(ay * f.rew_inv_W, 1.0f + __expf(f.rew_k * (ay - f.rew_y0)));
     code = BOATENV_TERM_NONE;
@@ -201,89 +177,132 @@ __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], in
     if (fabsf(s_r) > f.pi2) r -= 1.0f;
     reward = r;
 
+    acc[0] = a_x; acc[1] = a_y; acc[2] = a_r;
     d[D_VX] = v_x; d[D_VY] = v_y; d[D_VR] = v_r; d[D_RUDDER] = rudder;
     d[D_SX] = s_x; d[D_SY] = s_y; d[D_SR] = s_r; d[D_RET] += r;
+}
+
+// return_state  boat_env.py:308-326: the 11 normalised observations of an env, written to
+// its row of the warp's shared-memory staging tile.  `index` = Boat.index after the step.
+__device__ __forceinline__ void stage_obs(const DevCfg &c, double *row, const double (&d)[D_COUNT],
+                                          const double (&acc)[3], int index) {
+    const boatenv_params &p = c.p;
+    const double PI = 3.14159265358979323846;
+    row[0] = (d[D_SX] - 0.0) / (p.goal_line - 0.0);
+    row[1] = d[D_VX] / 5.0;
+    row[2] = acc[0] / 0.025;
+    row[3] = (d[D_SY] - (-p.track_width)) / (p.track_width - (-p.track_width));
+    row[4] = d[D_VY] / 2.0;
+    row[5] = acc[1] / 0.37;
+    row[6] = d[D_SR] / (2.0 * PI);
+    row[7] = d[D_VR] / 8.5e-3;
+    row[8] = acc[2] / 1.4e-5;
+    row[9] = (d[D_RUDDER] - (-PI / 3.0)) / (PI / 3.0 - (-PI / 3.0));
+    row[10] = (p.fuel - (double)index) / p.fuel;
+}
+__device__ __forceinline__ void stage_obs(const DevCfg &c, float *row, const float (&d)[D_COUNT],
+                                          const float (&acc)[3], int index) {
+    const FastConsts &f = c.f;
+    row[0] = d[D_SX] * f.inv_goal;
+    row[1] = d[D_VX] * f.inv_5;
+    row[2] = acc[0] * f.inv_ax;
+    row[3] = (d[D_SY] + f.W) * f.inv_2W;
+    row[4] = d[D_VY] * f.inv_2;
+    row[5] = acc[1] * f.inv_ay;
+    row[6] = d[D_SR] * f.inv_2pi;
+    row[7] = d[D_VR] * f.inv_vr;
+    row[8] = acc[2] * f.inv_ar;
+    row[9] = (d[D_RUDDER] + f.third_pi) * f.inv_rud;
+    row[10] = (f.fuel0 - (float)index) * f.inv_fuel;
 }
 
 // The reset observation (boat_env.py:124 after Boat.__init__): all zeros except s_y,
 // rudder (0.5) and fuel (1).
 template <typename T>
-__device__ __forceinline__ void reset_obs(const DevCfg &c, T s_y0, T (&obs)[kObsDim]) {
+__device__ __forceinline__ void stage_reset_obs(const DevCfg &c, T *row, T s_y0) {
 #pragma unroll
-    for (int k = 0; k < kObsDim; ++k) obs[k] = (T)0;
-    obs[3] = (T)(((double)s_y0 + c.p.track_width) / (c.p.track_width + c.p.track_width));
-    obs[9] = (T)0.5;
-    obs[10] = (T)1;
+    for (int k = 0; k < kObsDim; ++k) row[k] = (T)0;
+    row[3] = (T)(((double)s_y0 + c.p.track_width) / (c.p.track_width + c.p.track_width));
+    row[9] = (T)0.5;
+    row[10] = (T)1;
 }
 
-// Coalesced write of a CTA tile of [n][11] observations: stage in shared memory
-// (stride 11 is odd: conflict-free), then 128-bit stores of the contiguous tile.
+// Coalesced write of a warp's [rows][11] staging tile to rows [row0, row0 + rows) of a
+// row-major [n][11] global tensor: 128-bit stores of the contiguous 32 x 11 block.
 template <typename T>
-__device__ __forceinline__ void store_obs_tile(T *smem, T *gout, long long tile_base, int valid, const T (&obs)[kObsDim],
-                                               bool active) {
-    const int tid = threadIdx.x;
-    if (active) {
-#pragma unroll
-        for (int k = 0; k < kObsDim; ++k) smem[tid * kObsDim + k] = obs[k];
-    }
-    __syncthreads();
+__device__ __forceinline__ void copy_out_tile(const T *tile, T *gout, long long row0, int rows, int lane) {
     using V = typename VecOf<T>::type;
     constexpr int W = VecOf<T>::W;
-    const int nelem = valid * kObsDim;
-    const int nvec = nelem / W;
-    T *gbase = gout + tile_base * kObsDim;
-    V *gv = reinterpret_cast<V *>(gbase);
-    const V *sv = reinterpret_cast<const V *>(smem);
-    for (int v = tid; v < nvec; v += kTile) __stcs(gv + v, sv[v]);
-    for (int e = nvec * W + tid; e < nelem; e += kTile) gbase[e] = smem[e];
+    constexpr int NVEC = 32 * kObsDim / W;
+    T *g = gout + row0 * kObsDim;
+    if (rows == 32 && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+        V *gv = reinterpret_cast<V *>(g);
+        const V *sv = reinterpret_cast<const V *>(tile);
+#pragma unroll
+        for (int it = 0; it < (NVEC + 31) / 32; ++it) {
+            const int v = lane + 32 * it;
+            if (v < NVEC) __stcs(gv + v, sv[v]);
+        }
+    } else {
+        for (int e = lane; e < rows * kObsDim; e += 32) g[e] = tile[e];
+    }
 }
 
-template <typename T, int WK>
-__global__ void __launch_bounds__(kTile, 2)
-boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
-    __shared__ __align__(16) T obs_s[kTile * kObsDim];
-    __shared__ double scratch_s[kWarpsPerCta][kScratchDoubles];
-    __shared__ double cnt_s[kNumCounters];
+#ifndef BOAT_MINBLOCKS_F32
+#define BOAT_MINBLOCKS_F32 4  // 256-thread CTAs per SM the fp32 kernel is register-budgeted for
+#endif
+template <typename T> struct StepTuning;
+template <> struct StepTuning<float> { static constexpr int kMinBlocks = BOAT_MINBLOCKS_F32; };
+template <> struct StepTuning<double> { static constexpr int kMinBlocks = 1; };
 
+// One thread per env; every warp is self-contained (no CTA-wide barrier): it stages its 32
+// observation rows in its own shared-memory tile and serves its slow-path lanes itself.
+template <typename T, int WK>
+__global__ void __launch_bounds__(kTile, StepTuning<T>::kMinBlocks)
+boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
+    __shared__ __align__(16) T obs_s[kWarpsPerCta][32 * kObsDim];
+    __shared__ double scratch_s[kWarpsPerCta][kScratchDoubles];
+
+    constexpr bool kCurves = (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH);
     const unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long tile_base = a.env_begin + (long long)blockIdx.x * kTile;
-    const long long i = tile_base + tid;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row0 = a.env_begin + (long long)blockIdx.x * kTile + warp * 32;  // first env of this warp
+    if (row0 >= a.env_end) return;  // whole warp out of range
+    const long long i = row0 + lane;
     const bool active = i < a.env_end;
     const long long ii = active ? i : (a.env_end - 1);  // inactive lanes shadow the last env (no stores)
-    const int valid = (int)min((long long)kTile, a.env_end - tile_base);
-    if (tid < kNumCounters) cnt_s[tid] = 0.0;
+    const int rows = (int)min(32LL, a.env_end - row0);
+    T *tile = obs_s[warp];
+    T *row = tile + lane * kObsDim;
+    double *scratch = scratch_s[warp];
 
-    // ---- load: everything issued up front (6 independent 128-bit requests per thread) ----
+    // ---- load: everything issued up front (6 independent requests per thread) ----
     T d[D_COUNT];
     T wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
     load_group<T, D_COUNT>(c.dyn, c.n_envs, ii, d);
-    uint2 ix = __ldcs(c.idx + ii);
-    if (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH) load_group<T, 4>(c.windA, c.n_envs, ii, wa);
+    const uint2 ix = __ldcs(c.idx + ii);
+    if (kCurves) load_group<T, 4>(c.windA, c.n_envs, ii, wa);
     if (WK == WIND_BOTH) load_group<T, 4>(c.windB, c.n_envs, ii, wb);
     const T *act = reinterpret_cast<const T *>(a.actions);
     T action = __ldcs(act + ii);
-    __syncthreads();  // cnt_s zeroed
 
     int index = (int)ix.x;
     uint32_t episode = ix.y;
-    const T inv_Lm1 = (T)(1.0 / (double)c.Lm1);
-    T obs[kObsDim];
+    const T inv_Lm1 = sizeof(T) == 8 ? (T)c.inv_Lm1 : (T)c.f.inv_Lm1;
+    const bool auto_reset = (a.flags & BOATENV_AUTO_RESET) != 0;
     T rsum = (T)0;
     int code = BOATENV_TERM_NONE, nsteps = 0;
-    bool alive = true, wind_dirty = false, did_reset = false;
-    T final_obs[kObsDim];
+    bool alive = true, wind_dirty = false, next_stored = false;
 
     for (int k = 0; k < a.ksteps; ++k) {
         if (k > 0 && a.action_stride != 0) action = __ldcs(act + (long long)k * a.action_stride + ii);
         bool need_setup = false;
-        int index_next = 0;
         if (alive) {
             // ---- wind sample wind[index] from the carried piece coefficients ----
             T w = (T)0, th = (T)0;
             int j = 0, r = 0;
-            if (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH) {
-                piece_of(min(index, c.L - 1), c.npieces, c.Lm1, j, r);
+            if (kCurves) {
+                piece_of(c, min(index, c.L - 1), j, r);
                 const T s = (T)r * inv_Lm1;
                 const T va = ((wa[3] * s + wa[2]) * s + wa[1]) * s + wa[0];
                 if (WK == WIND_ANGLE_RECT) {
@@ -301,44 +320,53 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             }
             if (WK == WIND_CONST) { w = (T)c.p.max_velocity; th = (T)c.direction_rad; }
 
-            T rew;
-            substep<WK>(c, d, index, action, w, th, obs, rew, code);
+            T rew, acc[3];
+            substep<WK>(c, d, index, action, w, th, acc, rew, code);
             rsum += rew;
             ++nsteps;
             index += 1;
+            if (code != BOATENV_TERM_NONE || k == a.ksteps - 1) stage_obs(c, row, d, acc, index);
             if (code != BOATENV_TERM_NONE) {
                 alive = false;
                 need_setup = true;  // statistics, and the reset if AUTO_RESET
-            } else if (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH) {
+            } else if (kCurves) {
                 // does wind[index] (the next sub-step) live in the next spline piece?
                 if (r + c.npieces >= c.Lm1 && j + 1 <= c.npieces - 1) need_setup = true;
             }
-            index_next = index;
         }
         // ---- slow path: the warp serves its lanes one at a time ----
-        unsigned pending = __ballot_sync(FULL, need_setup && active);
-        if (pending) {
+        if (__ballot_sync(FULL, need_setup && active)) {
             const bool is_done = need_setup && active && code != BOATENV_TERM_NONE;
-            // statistics (info dict, boat_env.py:24-32,87-113)
             const unsigned dmask = __ballot_sync(FULL, is_done);
-            if (dmask) {
+            if (dmask) {  // statistics (info dict, boat_env.py:24-32,87-113): one atomic per counter per warp
+                double *cnt = c.counters + (blockIdx.x % kCounterSlots) * 32;
 #pragma unroll
                 for (int t = 1; t <= 5; ++t) {
                     const unsigned m = __ballot_sync(FULL, is_done && code == t);
-                    if (lane == 0 && m) atomicAdd(&cnt_s[t - 1], (double)__popc(m));
+                    if (lane == 0 && m) atomicAdd(cnt + (t - 1), (double)__popc(m));
                 }
                 const double ret = is_done ? (double)d[D_RET] : 0.0;
                 const double s1 = warp_sum(ret), s2 = warp_sum(ret * ret);
                 if (lane == 0) {
-                    atomicAdd(&cnt_s[5], (double)__popc(dmask));
-                    atomicAdd(&cnt_s[6], s1);
-                    atomicAdd(&cnt_s[7], s2);
+                    atomicAdd(cnt + 5, (double)__popc(dmask));
+                    atomicAdd(cnt + 6, s1);
+                    atomicAdd(cnt + 7, s2);
                 }
             }
-            const bool auto_reset = (a.flags & BOATENV_AUTO_RESET) != 0;
-            if (is_done) {
+            if (is_done) {  // the terminal observation leaves before a reset overwrites the row
+                if (a.final_obs_out) {
+                    T *fo = reinterpret_cast<T *>(a.final_obs_out) + i * kObsDim;
 #pragma unroll
-                for (int q = 0; q < kObsDim; ++q) final_obs[q] = obs[q];
+                    for (int q = 0; q < kObsDim; ++q) fo[q] = row[q];
+                }
+                if (a.rp.state) {  // s' of the fused store_transition (buffer.py:16)
+                    long long slot = a.rp.base_slot + i;
+                    if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
+                    T *s1 = reinterpret_cast<T *>(a.rp.new_state) + slot * kObsDim;
+#pragma unroll
+                    for (int q = 0; q < kObsDim; ++q) s1[q] = row[q];
+                    next_stored = true;
+                }
             }
             unsigned todo = __ballot_sync(FULL, need_setup && active && (!is_done || auto_reset));
             while (todo) {
@@ -347,67 +375,68 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                 const long long e_env = __shfl_sync(FULL, i, src);
                 const int e_done = __shfl_sync(FULL, (int)is_done, src);
                 const uint32_t e_epi = __shfl_sync(FULL, episode, src) + (e_done ? 1u : 0u);
-                const int e_idx = e_done ? 0 : __shfl_sync(FULL, index_next, src);
-                WindSetup ws;
-                wind_setup_warp(c, e_env, e_epi, e_idx, scratch_s[warp], ws);
+                const int e_idx = e_done ? 0 : __shfl_sync(FULL, index, src);
+                if (kCurves) wind_setup_warp(c, e_env, e_epi, e_idx, scratch);
                 if (lane == src) {
+                    if (kCurves) {
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) { wa[m] = (T)ws.a[m]; wb[m] = (T)ws.b[m]; }
-                    wind_dirty = true;
+                        for (int m = 0; m < 4; ++m) {
+                            wa[m] = (T)scratch[kCoefDoubles + m];
+                            wb[m] = (T)scratch[kCoefDoubles + 4 + m];
+                        }
+                        wind_dirty = true;
+                    }
                     if (e_done) {  // Boat.__init__  boat_env.py:144-201
 #pragma unroll
                         for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
-                        const T sy0 = (c.experiment == 2) ? (T)ws.s_y_start : (T)0;  // :166-167
+                        const T sy0 = (T)episode_start_y(c, i, e_epi);  // :166-167
                         d[D_SY] = sy0;
                         index = 0;
                         episode = e_epi;
-                        did_reset = true;
-                        reset_obs<T>(c, sy0, obs);
+                        stage_reset_obs<T>(c, row, sy0);
                     }
                 }
+                __syncwarp();  // scratch is reused by the next env of this warp
             }
         }
     }
 
     // ---- store ----
+    const bool done = code != BOATENV_TERM_NONE;
     if (active) {
         store_group<T, D_COUNT>(c.dyn, c.n_envs, i, d);
         __stcs(c.idx + i, make_uint2((uint32_t)index, episode));
         if (wind_dirty) {  // wind coefficients change only on the slow path
-            if (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH) store_group<T, 4>(c.windA, c.n_envs, i, wa);
+            if (kCurves) store_group<T, 4>(c.windA, c.n_envs, i, wa);
             if (WK == WIND_BOTH) store_group<T, 4>(c.windB, c.n_envs, i, wb);
         }
         __stcs(reinterpret_cast<T *>(a.reward_out) + i, rsum);
-        const bool done = code != BOATENV_TERM_NONE;
         a.done_out[i] = done ? 1 : 0;
         if (a.term_out) a.term_out[i] = (uint8_t)code;
         if (a.steps_out) a.steps_out[i] = nsteps;
-        if (done && a.final_obs_out) {
-            T *fo = reinterpret_cast<T *>(a.final_obs_out) + i * kObsDim;
-            const T *src = did_reset ? final_obs : obs;
-#pragma unroll
-            for (int q = 0; q < kObsDim; ++q) fo[q] = src[q];
+    }
+    __syncwarp();  // the warp's staging tile is complete
+    if (a.rp.state) {  // fused store_transition  buffer.py:13-22: ring slots of a warp are contiguous (mod size)
+        const unsigned skip = __ballot_sync(FULL, next_stored);
+        const T *prev = reinterpret_cast<const T *>(a.obs_in) + row0 * kObsDim;
+        T *ring_s = reinterpret_cast<T *>(a.rp.state), *ring_n = reinterpret_cast<T *>(a.rp.new_state);
+        for (int e = lane; e < rows * kObsDim; e += 32) {
+            const int rr = e / kObsDim, q = e - rr * kObsDim;
+            long long slot = a.rp.base_slot + row0 + rr;
+            if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
+            ring_s[slot * kObsDim + q] = prev[e];
+            if (!((skip >> rr) & 1u)) ring_n[slot * kObsDim + q] = tile[e];
         }
-        if (a.rp.state) {  // fused store_transition  buffer.py:13-22
-            const long long slot = (a.rp.base_cntr + i) % a.rp.mem_size;
-            const T *prev = reinterpret_cast<const T *>(a.obs_in) + i * kObsDim;
-            T *s0 = reinterpret_cast<T *>(a.rp.state) + slot * kObsDim;
-            T *s1 = reinterpret_cast<T *>(a.rp.new_state) + slot * kObsDim;
-            const T *nxt = (done && did_reset) ? final_obs : obs;
-#pragma unroll
-            for (int q = 0; q < kObsDim; ++q) { s0[q] = prev[q]; s1[q] = nxt[q]; }
+        if (active) {
+            long long slot = a.rp.base_slot + i;
+            if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
             reinterpret_cast<T *>(a.rp.action)[slot] = action;
             reinterpret_cast<T *>(a.rp.reward)[slot] = rsum;
             a.rp.terminal[slot] = a.rp.done_flag_mode ? (code == BOATENV_TERM_REACHED_GOAL) : done;
         }
+        __syncwarp();  // prev rows are read before the copy-out below overwrites them (obs_in may alias obs_out)
     }
-    store_obs_tile<T>(obs_s, reinterpret_cast<T *>(a.obs_out), tile_base, valid, obs, active);
-
-    // ---- flush statistics: one atomic per non-zero counter per CTA, 32 replicated rows ----
-    if (tid < kNumCounters) {
-        const double v = cnt_s[tid];
-        if (v != 0.0) atomicAdd(c.counters + (blockIdx.x % kCounterSlots) * 32 + tid, v);
-    }
+    copy_out_tile<T>(tile, reinterpret_cast<T *>(a.obs_out), row0, rows, lane);
 }
 
 }  // namespace boatenv

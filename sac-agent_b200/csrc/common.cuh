@@ -46,6 +46,7 @@ struct FastConsts {
         third_pi, inv_rud, inv_fuel;    // obs normalisers boat_env.py:308-326
     float fuel0, goal, oob, pi3, pi4, pi2;
     float rew_inv_W, rew_k, rew_y0;     // reward_functions.py:52-54
+    float inv_Lm1;                      // 1 / (L - 1): wind sample index -> local spline coordinate
 };
 
 struct DevCfg {
@@ -55,6 +56,8 @@ struct DevCfg {
     int experiment, wind_kind, test_mode, ncurves;
     int fp, npieces;          // wind.fixed_points and fp - 1
     int L, Lm1;               // wind table length int(t_max/dt) (wind.py:14-15), L - 1
+    unsigned magic_m, magic_s;  // floor(n / Lm1) == __umulhi(n, magic_m) >> magic_s for n <= L * npieces
+    double inv_Lm1;           // 1.0 / Lm1
     int timeout_steps;        // first step count n with accumulated t >= t_max (boat_env.py:98)
     int s_y_half;             // int(track_width * 0.8) (boat_env.py:148-149)
     boatenv_params p;         // raw reference parameters (fp64 validation mode uses these)
@@ -74,7 +77,7 @@ struct DevCfg {
 struct ReplayView {   // fused agent.remember (main.py:83-88, buffer.py:13-22); null = off
     void *state, *new_state, *action, *reward;
     uint8_t *terminal;
-    long long mem_size, base_cntr;
+    long long mem_size, base_slot;   // base_slot = mem_cntr % mem_size: env i goes to slot base_slot + i (mod size)
     int done_flag_mode;
 };
 

@@ -264,7 +264,7 @@ int boatenv_step_store(boatenv_t h, boatreplay_t r, const void *actions, void *o
     a.rp.reward = r->reward;
     a.rp.terminal = r->terminal;
     a.rp.mem_size = r->mem_size;
-    a.rp.base_cntr = r->mem_cntr;
+    a.rp.base_slot = r->mem_cntr % r->mem_size;
     a.rp.done_flag_mode = done_flag_mode;
     CUDA_TRY(r->precision == 32 ? launch_step_f32(c, a, (cudaStream_t)stream)
                                 : launch_step_f64(c, a, (cudaStream_t)stream));

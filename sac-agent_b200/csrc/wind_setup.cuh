@@ -19,45 +19,40 @@
 
 namespace boatenv {
 
-constexpr int kScratchDoubles = 2 * (kMaxKnots - 1) * 4;  // per warp: [curve][piece][4]
+constexpr int kCoefDoubles = 2 * (kMaxKnots - 1) * 4;  // per warp: [curve][piece][4]
+constexpr int kScratchDoubles = kCoefDoubles + 8;      // + the folded result: a[4], b[4]
 
-struct WindSetup {
-    double a[4];  // first drawn curve  (exp 4/6: velocity, exp 5: rect source)
-    double b[4];  // second drawn curve (exp 6: angle)
-    int s_y_start;
-};
-
-// Piece index and local coordinate s in [0,1] of wind sample `index`:
-// x_index / h = index * (fp-1) / (L-1) exactly (x_index = index * L/(L-1), h = L/(fp-1)).
-__device__ __forceinline__ void piece_of(int index, int npieces, int Lm1, int &j, int &r) {
-    int num = index * npieces;
-    j = num / Lm1;
-    if (j > npieces - 1) j = npieces - 1;
-    r = num - j * Lm1;
+// Piece index and local coordinate numerator of wind sample `index` (0 <= index < L):
+// x_index / h = index * (fp-1) / (L-1) exactly (x_index = index * L/(L-1), h = L/(fp-1)),
+// so piece j = floor(index * npieces / Lm1) (capped) and s = r / Lm1 with r the remainder.
+// The division is a multiply-high by a host-derived magic number (exact on this range).
+__device__ __forceinline__ void piece_of(const DevCfg &c, int index, int &j, int &r) {
+    const uint32_t num = (uint32_t)index * (uint32_t)c.npieces;
+    uint32_t q = __umulhi(num, c.magic_m) >> c.magic_s;
+    q = min(q, (uint32_t)(c.npieces - 1));
+    j = (int)q;
+    r = (int)(num - q * (uint32_t)c.Lm1);
 }
 
-__device__ __forceinline__ double eval_sample(const double *scratch, int curve, int index, int npieces, int Lm1,
-                                              int L) {
-    index = max(0, min(index, L - 1));
+__device__ __forceinline__ double eval_sample(const DevCfg &c, const double *scratch, int curve, int index) {
+    index = max(0, min(index, c.L - 1));
     int j, r;
-    piece_of(index, npieces, Lm1, j, r);
-    const double s = (double)r / (double)Lm1;
-    const double *cf = scratch + (curve * npieces + j) * 4;
+    piece_of(c, index, j, r);
+    const double s = (double)r * c.inv_Lm1;
+    const double *cf = scratch + (curve * c.npieces + j) * 4;
     return fma(fma(fma(cf[3], s, cf[2]), s, cf[1]), s, cf[0]);
 }
 
-// Called by all 32 lanes with warp-uniform arguments.
-static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long env_local, uint32_t episode, int index_next,
-                                             double *scratch, WindSetup &out) {
+// Called by all 32 lanes with warp-uniform arguments.  On return scratch[kCoefDoubles + m]
+// (m = 0..3) holds the folded coefficients of the first drawn curve's piece containing
+// sample `index_next` (exp 4/6: velocity, exp 5: the rect source) and [.. + 4 + m] those of
+// the second drawn curve (exp 6: angle).  The caller must __syncwarp() before the next call.
+static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long env_local, uint32_t episode,
+                                                    int index_next, double *scratch) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int fp = c.fp, np = c.npieces, nc = c.ncurves;
     const long long genv = c.env_id_offset + env_local;
-
-    out.s_y_start = c.ovr_s_y ? c.ovr_s_y[env_local] : episode_s_y_start(c.seed, genv, episode, c.s_y_half);
-#pragma unroll
-    for (int m = 0; m < 4; ++m) { out.a[m] = 0.0; out.b[m] = 0.0; }
-    if (nc == 0) return;
 
     // --- knots: one per lane -----------------------------------------------------
     double u = 0.0;
@@ -70,7 +65,7 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
         const int t = base + lane;
         const bool valid = t < total;
         const int tt = valid ? t : 0;
-        const int curve = tt / (np * 4);
+        const int curve = (tt >= np * 4) ? 1 : 0;
         const int rem = tt - curve * np * 4;
         const double *row = c.basis + (size_t)rem * fp;  // rem = piece * 4 + m
         double acc = 0.0;
@@ -85,13 +80,13 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
     // --- extremal samples of every piece -------------------------------------------
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     double mn = inf, mx = -inf;
-    const int my_curve = lane / np;
+    const int my_curve = (lane >= np) ? 1 : 0;
     if (lane < nc * np) {
         const int j = lane - my_curve * np;
         const double *cf = scratch + (my_curve * np + j) * 4;
         const double c1 = cf[1], c2 = cf[2], c3 = cf[3];
         auto consider = [&](int index) {
-            const double v = eval_sample(scratch, my_curve, index, np, c.Lm1, c.L);
+            const double v = eval_sample(c, scratch, my_curve, index);
             mn = fmin(mn, v);
             mx = fmax(mx, v);
         };
@@ -133,31 +128,30 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
         mxB = warp_max(inB ? mx : -inf);
     }
 
-    // --- fold renormalisation (wind.py:87-89) and the experiment's scale -------------
+    // --- fold renormalisation (wind.py:87-89) and the experiment's scale: lanes 0..7 --
     int jn, rn;
-    piece_of(min(index_next, c.L - 1), np, c.Lm1, jn, rn);
-    {
-        const double *cf = scratch + (0 * np + jn) * 4;
+    piece_of(c, min(index_next, c.L - 1), jn, rn);
+    if (lane < 4 * nc) {
+        const int curve = lane >> 2, m = lane & 3;
+        const double cf = scratch[(curve * np + jn) * 4 + m];
+        const double lo = curve ? mnB : mnA, hi = curve ? mxB : mxA;
         double off = 0.0, inv = 1.0;
-        if (mnA < 0.0 || mxA > 1.0) { off = mnA; inv = 1.0 / (mxA - mnA); }
-        // exp 4 / 6: curve * max_velocity (wind.py:49,62); exp 5: rect threshold on the curve itself
-        const double scale = (c.wind_kind == WIND_ANGLE_RECT) ? 1.0 : c.p.max_velocity;
-        out.a[0] = (cf[0] - off) * inv * scale;
-        out.a[1] = cf[1] * inv * scale;
-        out.a[2] = cf[2] * inv * scale;
-        out.a[3] = cf[3] * inv * scale;
+        if (lo < 0.0 || hi > 1.0) { off = lo; inv = 1.0 / (hi - lo); }
+        // exp 4 / 6: curve * max_velocity (wind.py:49,62); exp 5: the rect threshold acts on the curve
+        // itself; second curve of exp 6: curve * pi * 2 (wind.py:63)
+        const double scale = curve ? 3.14159265358979323846 * 2.0
+                                   : ((c.wind_kind == WIND_ANGLE_RECT) ? 1.0 : c.p.max_velocity);
+        scratch[kCoefDoubles + lane] = ((m == 0) ? (cf - off) : cf) * inv * scale;
+    } else if (lane < 8) {
+        scratch[kCoefDoubles + lane] = 0.0;
     }
-    if (nc == 2) {
-        const double *cf = scratch + (1 * np + jn) * 4;
-        double off = 0.0, inv = 1.0;
-        if (mnB < 0.0 || mxB > 1.0) { off = mnB; inv = 1.0 / (mxB - mnB); }
-        const double scale = 3.14159265358979323846 * 2.0;  // curve * pi * 2 (wind.py:63)
-        out.b[0] = (cf[0] - off) * inv * scale;
-        out.b[1] = cf[1] * inv * scale;
-        out.b[2] = cf[2] * inv * scale;
-        out.b[3] = cf[3] * inv * scale;
-    }
-    __syncwarp();  // scratch is reused by the next env of this warp
+    __syncwarp();
+}
+
+// np.random.randint draw of an episode (boat_env.py:147-150): only experiment 2 uses it.
+__device__ __forceinline__ int episode_start_y(const DevCfg &c, long long env_local, uint32_t episode) {
+    if (c.experiment != 2) return 0;  // boat_env.py:166-170: v_y_integrator initial_value = 0 otherwise
+    return c.ovr_s_y ? c.ovr_s_y[env_local] : episode_s_y_start(c.seed, c.env_id_offset + env_local, episode, c.s_y_half);
 }
 
 }  // namespace boatenv
