@@ -252,18 +252,22 @@ int boatenv_create(const boatenv_params *params, int64_t n_envs, uint64_t seed, 
     const size_t n = (size_t)n_envs;
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
-    alloc(&cfg.dyn, n * D_COUNT * h->esize);
-    alloc((void **)&cfg.idx, n * sizeof(uint2));
-    if (cfg.ncurves >= 1) alloc(&cfg.windA, n * 4 * h->esize);
-    if (cfg.ncurves >= 2) alloc(&cfg.windB, n * 4 * h->esize);
+    {   // tile-blocked state: [dyn][idx][wind A][wind B] sections per 32-env block (common.cuh)
+        const int nd = D_COUNT * (int)h->esize / 16, nw = 4 * (int)h->esize / 16;
+        cfg.off_idx = 32 * 16 * nd;
+        cfg.off_wa = cfg.off_idx + 32 * 8;
+        cfg.off_wb = cfg.off_wa + (cfg.ncurves >= 1 ? 32 * 16 * nw : 0);
+        cfg.block_bytes = cfg.off_wb + (cfg.ncurves >= 2 ? 32 * 16 * nw : 0);
+    }
+    const size_t state_bytes = (size_t)num_blocks(n_envs) * (size_t)cfg.block_bytes;
+    alloc((void **)&cfg.state, state_bytes);
     alloc((void **)&cfg.counters, kCounterSlots * 32 * sizeof(double));
     alloc((void **)&h->counters_out_dev, kNumCounters * sizeof(double));
     std::vector<double> basis;
     compute_spline_basis(cfg.fp, basis);
     alloc((void **)&h->basis_dev, basis.size() * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(h->basis_dev, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(cfg.dyn, 0, n * D_COUNT * h->esize);
-    if (e == cudaSuccess) e = cudaMemset(cfg.idx, 0xFF, n * sizeof(uint2));  // episode -1: reset() makes it 0
+    if (e == cudaSuccess) e = cudaMemset(cfg.state, 0xFF, state_bytes);  // episode -1: reset() makes it 0
     if (e == cudaSuccess) e = cudaMemset(cfg.counters, 0, kCounterSlots * 32 * sizeof(double));
     cfg.basis = h->basis_dev;
     h->cfg = cfg;
@@ -278,10 +282,7 @@ int boatenv_create(const boatenv_params *params, int64_t n_envs, uint64_t seed, 
 int boatenv_destroy(boatenv_t h) {
     if (!h) return BOATENV_EINVAL;
     cudaSetDevice(h->device);
-    cudaFree(h->cfg.dyn);
-    cudaFree(h->cfg.idx);
-    cudaFree(h->cfg.windA);
-    cudaFree(h->cfg.windB);
+    cudaFree(h->cfg.state);
     cudaFree(h->cfg.counters);
     cudaFree(h->counters_out_dev);
     cudaFree(h->basis_dev);

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(kTile) boat_reset_kernel(const __grid_constant
     const bool active = i < c.n_envs;
     const bool want = active && (mask == nullptr || mask[i] != 0);
     uint32_t episode = 0;
-    if (want) episode = c.idx[i].y + 1u;
+    if (want) episode = reinterpret_cast<const uint2 *>(block_section(c, i, c.off_idx))[lane].y + 1u;
     unsigned todo = __ballot_sync(FULL, want);
     while (todo) {
         const int src = __ffs(todo) - 1;
@@ -36,10 +36,10 @@ __global__ void __launch_bounds__(kTile) boat_reset_kernel(const __grid_constant
                 wa[m] = c.ncurves > 0 ? (T)scratch_s[warp][kCoefDoubles + m] : (T)0;
                 wb[m] = c.ncurves > 0 ? (T)scratch_s[warp][kCoefDoubles + 4 + m] : (T)0;
             }
-            store_group<T, D_COUNT>(c.dyn, c.n_envs, i, d);
-            c.idx[i] = make_uint2(0u, e_epi);
-            if (c.windA) store_group<T, 4>(c.windA, c.n_envs, i, wa);
-            if (c.windB) store_group<T, 4>(c.windB, c.n_envs, i, wb);
+            store_vecs<T, D_COUNT>(block_section(c, i, 0), lane, d);
+            reinterpret_cast<uint2 *>(block_section(c, i, c.off_idx))[lane] = make_uint2(0u, e_epi);
+            if (c.ncurves >= 1) store_vecs<T, 4>(block_section(c, i, c.off_wa), lane, wa);
+            if (c.ncurves >= 2) store_vecs<T, 4>(block_section(c, i, c.off_wb), lane, wb);
             if (obs_out) {
                 stage_reset_obs<T>(c, obs, sy0);
 #pragma unroll
@@ -59,7 +59,7 @@ static __global__ void __launch_bounds__(32) boat_wind_table_kernel(const __grid
     __shared__ double folded[kMaxKnots - 1][8];
     const int lane = threadIdx.x;
     const double PI = 3.14159265358979323846;
-    const uint32_t episode = c.idx[env].y;
+    const uint32_t episode = reinterpret_cast<const uint2 *>(block_section(c, env, c.off_idx))[env & 31].y;
     if (c.ncurves > 0) {
         for (int j = 0; j < c.npieces; ++j) {
             const int first_index = (j * c.Lm1 + c.npieces - 1) / c.npieces;
@@ -92,16 +92,21 @@ static __global__ void __launch_bounds__(32) boat_wind_table_kernel(const __grid
     }
 }
 
+// Scalar `field` (DynSlot order) of env i inside its block: vector row field / VW, slot field % VW.
+template <typename T>
+__device__ __forceinline__ T *dyn_scalar(const DevCfg &c, long long i, int field) {
+    constexpr int W = VecOf<T>::W;
+    return reinterpret_cast<T *>(block_section(c, i, 0)) + ((field / W) * 32 + (int)(i & 31)) * W + (field % W);
+}
+
 template <typename T>
 __global__ void boat_get_field_kernel(const __grid_constant__ DevCfg c, int field, void *out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n_envs) return;
     if (field < D_COUNT) {
-        constexpr int W = VecOf<T>::W;
-        const T *base = reinterpret_cast<const T *>(c.dyn);
-        reinterpret_cast<T *>(out)[i] = base[((long long)(field / W) * c.n_envs + i) * W + (field % W)];
+        reinterpret_cast<T *>(out)[i] = *dyn_scalar<T>(c, i, field);
     } else {
-        const uint2 v = c.idx[i];
+        const uint2 v = reinterpret_cast<const uint2 *>(block_section(c, i, c.off_idx))[i & 31];
         reinterpret_cast<uint32_t *>(out)[i] = (field == BOATENV_F_STEP_INDEX) ? v.x : v.y;
     }
 }
@@ -111,14 +116,13 @@ __global__ void boat_set_field_kernel(const __grid_constant__ DevCfg c, int fiel
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n_envs) return;
     if (field < D_COUNT) {
-        constexpr int W = VecOf<T>::W;
-        T *base = reinterpret_cast<T *>(c.dyn);
-        base[((long long)(field / W) * c.n_envs + i) * W + (field % W)] = reinterpret_cast<const T *>(in)[i];
+        *dyn_scalar<T>(c, i, field) = reinterpret_cast<const T *>(in)[i];
     } else {
-        uint2 v = c.idx[i];
+        uint2 *p = reinterpret_cast<uint2 *>(block_section(c, i, c.off_idx)) + (i & 31);
+        uint2 v = *p;
         const uint32_t x = reinterpret_cast<const uint32_t *>(in)[i];
         if (field == BOATENV_F_STEP_INDEX) v.x = x; else v.y = x;
-        c.idx[i] = v;
+        *p = v;
     }
 }
 

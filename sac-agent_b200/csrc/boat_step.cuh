@@ -248,195 +248,327 @@ __device__ __forceinline__ void copy_out_tile(const T *tile, T *gout, long long 
     }
 }
 
+// ---------------------------------------------------------------------------------
+// TMA bulk-copy + mbarrier primitives (sm_90+/sm_100a PTX).  The copies are 1-D
+// (cp.async.bulk, no tensor map): a warp's state block is contiguous in HBM.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on `bar`; L2 evict-first (streamed once)
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the bulk stores of all committed groups have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes (st.shared) -> visible to the async proxy (the bulk store that follows)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 #ifndef BOAT_MINBLOCKS_F32
-#define BOAT_MINBLOCKS_F32 4  // 256-thread CTAs per SM the fp32 kernel is register-budgeted for
+#define BOAT_MINBLOCKS_F32 2  // 256-thread CTAs per SM the fp32 kernel is register-budgeted for
+#endif
+#ifndef BOAT_STAGES
+#define BOAT_STAGES 3         // state blocks in flight per warp (TMA pipeline depth)
 #endif
 template <typename T> struct StepTuning;
 template <> struct StepTuning<float> { static constexpr int kMinBlocks = BOAT_MINBLOCKS_F32; };
 template <> struct StepTuning<double> { static constexpr int kMinBlocks = 1; };
+constexpr int kStages = BOAT_STAGES;
 
-// One thread per env; every warp is self-contained (no CTA-wide barrier): it stages its 32
-// observation rows in its own shared-memory tile and serves its slow-path lanes itself.
+// Shared memory of one warp (dynamic smem, carved per warp): the TMA stages, the observation
+// staging tile, the slow-path scratch and the stage barriers.
+template <typename T>
+__host__ __device__ constexpr int warp_smem_bytes(int block_bytes) {
+    return (kStages * block_bytes + 32 * kObsDim * (int)sizeof(T) + kScratchDoubles * 8 + kStages * 8 + 127) / 128 * 128;
+}
+
+// Persistent kernel, one thread per env, every warp self-contained: warp w walks the 32-env
+// state blocks w, w + W, w + 2W, ... (W = warps in the grid).  Its lane 0 keeps kStages TMA
+// bulk copies of upcoming blocks in flight (mbarrier-completed), so the HBM latency is hidden
+// by the pipeline instead of by occupancy; lanes read their state from shared memory, run the
+// K sub-steps in registers, write the state back with coalesced 128-bit stores and the
+// [32][11] observation tile with one bulk store.  No CTA-wide barrier anywhere.
 template <typename T, int WK>
 __global__ void __launch_bounds__(kTile, StepTuning<T>::kMinBlocks)
 boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
-    __shared__ __align__(16) T obs_s[kWarpsPerCta][32 * kObsDim];
-    __shared__ double scratch_s[kWarpsPerCta][kScratchDoubles];
-
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool kCurves = (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH);
+    constexpr int kTileBytes = 32 * kObsDim * (int)sizeof(T);
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long row0 = a.env_begin + (long long)blockIdx.x * kTile + warp * 32;  // first env of this warp
-    if (row0 >= a.env_end) return;  // whole warp out of range
-    const long long i = row0 + lane;
-    const bool active = i < a.env_end;
-    const long long ii = active ? i : (a.env_end - 1);  // inactive lanes shadow the last env (no stores)
-    const int rows = (int)min(32LL, a.env_end - row0);
-    T *tile = obs_s[warp];
+    const int bb = c.block_bytes;
+
+    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<T>(bb);
+    unsigned char *stage_base = wbase;                                  // kStages * bb   (16-byte aligned)
+    T *tile = reinterpret_cast<T *>(wbase + kStages * bb);              // [32][11]
+    double *scratch = reinterpret_cast<double *>(wbase + kStages * bb + kTileBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(wbase + kStages * bb + kTileBytes + kScratchDoubles * 8);
     T *row = tile + lane * kObsDim;
-    double *scratch = scratch_s[warp];
 
-    // ---- load: everything issued up front (6 independent requests per thread) ----
-    T d[D_COUNT];
-    T wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
-    load_group<T, D_COUNT>(c.dyn, c.n_envs, ii, d);
-    const uint2 ix = __ldcs(c.idx + ii);
-    if (kCurves) load_group<T, 4>(c.windA, c.n_envs, ii, wa);
-    if (WK == WIND_BOTH) load_group<T, 4>(c.windB, c.n_envs, ii, wb);
+    const long long blk_begin = a.env_begin >> 5, blk_end = (a.env_end + 31) >> 5;
+    const long long wstride = (long long)gridDim.x * kWarpsPerCta;
+    long long blk = blk_begin + (long long)blockIdx.x * kWarpsPerCta + warp;
+    if (blk >= blk_end) return;
+
+    const uint64_t pol = policy_evict_first();
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    if (lane == 0) {  // prologue: fill the pipeline
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            const long long b = blk + s * wstride;
+            if (b < blk_end) {
+                mbar_expect_tx(full + s, (uint32_t)bb);
+                tma_load_1d(stage_base + s * bb, c.state + b * (long long)bb, (uint32_t)bb, full + s, pol);
+            }
+        }
+    }
     const T *act = reinterpret_cast<const T *>(a.actions);
-    T action = __ldcs(act + ii);
-
-    int index = (int)ix.x;
-    uint32_t episode = ix.y;
     const T inv_Lm1 = sizeof(T) == 8 ? (T)c.inv_Lm1 : (T)c.f.inv_Lm1;
     const bool auto_reset = (a.flags & BOATENV_AUTO_RESET) != 0;
-    T rsum = (T)0;
-    int code = BOATENV_TERM_NONE, nsteps = 0;
-    bool alive = true, wind_dirty = false, next_stored = false;
+    T action_next = __ldcs(act + min(blk * 32 + lane, a.env_end - 1));
+    int stage = 0;
+    uint32_t parity = 0;
+    bool tile_in_flight = false;  // a bulk store of `tile` may still be reading it
 
-    for (int k = 0; k < a.ksteps; ++k) {
-        if (k > 0 && a.action_stride != 0) action = __ldcs(act + (long long)k * a.action_stride + ii);
-        bool need_setup = false;
-        if (alive) {
-            // ---- wind sample wind[index] from the carried piece coefficients ----
-            T w = (T)0, th = (T)0;
-            int j = 0, r = 0;
-            if (kCurves) {
-                piece_of(c, min(index, c.L - 1), j, r);
-                const T s = (T)r * inv_Lm1;
-                const T va = ((wa[3] * s + wa[2]) * s + wa[1]) * s + wa[0];
-                if (WK == WIND_ANGLE_RECT) {
-                    if (sizeof(T) == 8) {  // wind.py:57-58,95: (value<=0.25 ? 0 : 1)*pi + pi/2
-                        w = (T)c.p.max_velocity;
-                        th = (T)(((double)va <= 0.25 ? 0.0 : 1.0) * 3.14159265358979323846 + 3.14159265358979323846 / 2.0);
-                    } else {
-                        th = va;  // the fp32 path thresholds inside substep()
-                    }
-                } else {
-                    w = va;
-                    th = (T)c.direction_rad;
-                }
-                if (WK == WIND_BOTH) th = ((wb[3] * s + wb[2]) * s + wb[1]) * s + wb[0];
-            }
-            if (WK == WIND_CONST) { w = (T)c.p.max_velocity; th = (T)c.direction_rad; }
+    for (; blk < blk_end; blk += wstride) {
+        const long long row0 = blk * 32;
+        const long long i = row0 + lane;
+        const bool active = i < a.env_end;  // inactive lanes are the padding of the last block (no stores)
+        const int rows = (int)min(32LL, a.env_end - row0);
+        T action = action_next;
+        if (blk + wstride < blk_end) action_next = __ldcs(act + min((blk + wstride) * 32 + lane, a.env_end - 1));
 
-            T rew, acc[3];
-            substep<WK>(c, d, index, action, w, th, acc, rew, code);
-            rsum += rew;
-            ++nsteps;
-            index += 1;
-            if (code != BOATENV_TERM_NONE || k == a.ksteps - 1) stage_obs(c, row, d, acc, index);
-            if (code != BOATENV_TERM_NONE) {
-                alive = false;
-                need_setup = true;  // statistics, and the reset if AUTO_RESET
-            } else if (kCurves) {
-                // does wind[index] (the next sub-step) live in the next spline piece?
-                if (r + c.npieces >= c.Lm1 && j + 1 <= c.npieces - 1) need_setup = true;
+        // ---- state: wait for the TMA copy of this block, read it from shared memory ----
+        const unsigned char *sb = stage_base + stage * bb;
+        mbar_wait(full + stage, parity);
+        T d[D_COUNT];
+        T wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
+        load_vecs<T, D_COUNT>(reinterpret_cast<const char *>(sb), lane, d);
+        if (kCurves) load_vecs<T, 4>(reinterpret_cast<const char *>(sb) + c.off_wa, lane, wa);
+        if (WK == WIND_BOTH) load_vecs<T, 4>(reinterpret_cast<const char *>(sb) + c.off_wb, lane, wb);
+        const uint2 ix = reinterpret_cast<const uint2 *>(sb + c.off_idx)[lane];  // last LDS of the stage
+        int index = (int)ix.x;
+        uint32_t episode = ix.y;
+        __syncwarp();
+        if (lane == 0) {
+            // The stage is consumed: refill it kStages blocks ahead.  The block number carries a data
+            // dependency on the LAST shared-memory load of the stage (bit 31 of the step index is never
+            // set), so the bulk copy cannot be issued before the warp's loads have returned.
+            const long long b = blk + (long long)kStages * wstride + (long long)(ix.x >> 31);
+            if (b < blk_end) {
+                mbar_expect_tx(full + stage, (uint32_t)bb);
+                tma_load_1d(stage_base + stage * bb, c.state + b * (long long)bb, (uint32_t)bb, full + stage, pol);
             }
         }
-        // ---- slow path: the warp serves its lanes one at a time ----
-        if (__ballot_sync(FULL, need_setup && active)) {
-            const bool is_done = need_setup && active && code != BOATENV_TERM_NONE;
-            const unsigned dmask = __ballot_sync(FULL, is_done);
-            if (dmask) {  // statistics (info dict, boat_env.py:24-32,87-113): one atomic per counter per warp
-                double *cnt = c.counters + (blockIdx.x % kCounterSlots) * 32;
-#pragma unroll
-                for (int t = 1; t <= 5; ++t) {
-                    const unsigned m = __ballot_sync(FULL, is_done && code == t);
-                    if (lane == 0 && m) atomicAdd(cnt + (t - 1), (double)__popc(m));
-                }
-                const double ret = is_done ? (double)d[D_RET] : 0.0;
-                const double s1 = warp_sum(ret), s2 = warp_sum(ret * ret);
-                if (lane == 0) {
-                    atomicAdd(cnt + 5, (double)__popc(dmask));
-                    atomicAdd(cnt + 6, s1);
-                    atomicAdd(cnt + 7, s2);
-                }
-            }
-            if (is_done) {  // the terminal observation leaves before a reset overwrites the row
-                if (a.final_obs_out) {
-                    T *fo = reinterpret_cast<T *>(a.final_obs_out) + i * kObsDim;
-#pragma unroll
-                    for (int q = 0; q < kObsDim; ++q) fo[q] = row[q];
-                }
-                if (a.rp.state) {  // s' of the fused store_transition (buffer.py:16)
-                    long long slot = a.rp.base_slot + i;
-                    if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
-                    T *s1 = reinterpret_cast<T *>(a.rp.new_state) + slot * kObsDim;
-#pragma unroll
-                    for (int q = 0; q < kObsDim; ++q) s1[q] = row[q];
-                    next_stored = true;
-                }
-            }
-            unsigned todo = __ballot_sync(FULL, need_setup && active && (!is_done || auto_reset));
-            while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const long long e_env = __shfl_sync(FULL, i, src);
-                const int e_done = __shfl_sync(FULL, (int)is_done, src);
-                const uint32_t e_epi = __shfl_sync(FULL, episode, src) + (e_done ? 1u : 0u);
-                const int e_idx = e_done ? 0 : __shfl_sync(FULL, index, src);
-                if (kCurves) wind_setup_warp(c, e_env, e_epi, e_idx, scratch);
-                if (lane == src) {
-                    if (kCurves) {
-#pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            wa[m] = (T)scratch[kCoefDoubles + m];
-                            wb[m] = (T)scratch[kCoefDoubles + 4 + m];
+        if (++stage == kStages) { stage = 0; parity ^= 1u; }
+
+        T rsum = (T)0;
+        int code = BOATENV_TERM_NONE, nsteps = 0;
+        bool alive = true, wind_dirty = false, next_stored = false;
+        if (tile_in_flight) {  // the previous block's observation bulk store must be done reading `tile`
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+            tile_in_flight = false;
+        }
+
+        for (int k = 0; k < a.ksteps; ++k) {
+            if (k > 0 && a.action_stride != 0) action = __ldcs(act + (long long)k * a.action_stride + min(i, a.env_end - 1));
+            bool need_setup = false;
+            if (alive) {
+                // ---- wind sample wind[index] from the carried piece coefficients ----
+                T w = (T)0, th = (T)0;
+                int j = 0, r = 0;
+                if (kCurves) {
+                    piece_of(c, min(index, c.L - 1), j, r);
+                    const T s = (T)r * inv_Lm1;
+                    const T va = ((wa[3] * s + wa[2]) * s + wa[1]) * s + wa[0];
+                    if (WK == WIND_ANGLE_RECT) {
+                        if (sizeof(T) == 8) {  // wind.py:57-58,95: (value<=0.25 ? 0 : 1)*pi + pi/2
+                            w = (T)c.p.max_velocity;
+                            th = (T)(((double)va <= 0.25 ? 0.0 : 1.0) * 3.14159265358979323846 + 3.14159265358979323846 / 2.0);
+                        } else {
+                            th = va;  // the fp32 path thresholds inside substep()
                         }
-                        wind_dirty = true;
+                    } else {
+                        w = va;
+                        th = (T)c.direction_rad;
                     }
-                    if (e_done) {  // Boat.__init__  boat_env.py:144-201
+                    if (WK == WIND_BOTH) th = ((wb[3] * s + wb[2]) * s + wb[1]) * s + wb[0];
+                }
+                if (WK == WIND_CONST) { w = (T)c.p.max_velocity; th = (T)c.direction_rad; }
+
+                T rew, acc[3];
+                substep<WK>(c, d, index, action, w, th, acc, rew, code);
+                rsum += rew;
+                ++nsteps;
+                index += 1;
+                if (code != BOATENV_TERM_NONE || k == a.ksteps - 1) stage_obs(c, row, d, acc, index);
+                if (code != BOATENV_TERM_NONE) {
+                    alive = false;
+                    need_setup = true;  // statistics, and the reset if AUTO_RESET
+                } else if (kCurves) {
+                    // does wind[index] (the next sub-step) live in the next spline piece?
+                    if (r + c.npieces >= c.Lm1 && j + 1 <= c.npieces - 1) need_setup = true;
+                }
+            }
+            // ---- slow path: the warp serves its lanes one at a time ----
+            if (__ballot_sync(FULL, need_setup && active)) {
+                const bool is_done = need_setup && active && code != BOATENV_TERM_NONE;
+                const unsigned dmask = __ballot_sync(FULL, is_done);
+                if (dmask) {  // statistics (info dict, boat_env.py:24-32,87-113): one atomic per counter per warp
+                    double *cnt = c.counters + (int)(blk % kCounterSlots) * 32;
 #pragma unroll
-                        for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
-                        const T sy0 = (T)episode_start_y(c, i, e_epi);  // :166-167
-                        d[D_SY] = sy0;
-                        index = 0;
-                        episode = e_epi;
-                        stage_reset_obs<T>(c, row, sy0);
+                    for (int t = 1; t <= 5; ++t) {
+                        const unsigned m = __ballot_sync(FULL, is_done && code == t);
+                        if (lane == 0 && m) atomicAdd(cnt + (t - 1), (double)__popc(m));
+                    }
+                    const double ret = is_done ? (double)d[D_RET] : 0.0;
+                    const double s1 = warp_sum(ret), s2 = warp_sum(ret * ret);
+                    if (lane == 0) {
+                        atomicAdd(cnt + 5, (double)__popc(dmask));
+                        atomicAdd(cnt + 6, s1);
+                        atomicAdd(cnt + 7, s2);
                     }
                 }
-                __syncwarp();  // scratch is reused by the next env of this warp
+                if (is_done) {  // the terminal observation leaves before a reset overwrites the row
+                    if (a.final_obs_out) {
+                        T *fo = reinterpret_cast<T *>(a.final_obs_out) + i * kObsDim;
+#pragma unroll
+                        for (int q = 0; q < kObsDim; ++q) fo[q] = row[q];
+                    }
+                    if (a.rp.state) {  // s' of the fused store_transition (buffer.py:16)
+                        long long slot = a.rp.base_slot + i;
+                        if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
+                        T *s1 = reinterpret_cast<T *>(a.rp.new_state) + slot * kObsDim;
+#pragma unroll
+                        for (int q = 0; q < kObsDim; ++q) s1[q] = row[q];
+                        next_stored = true;
+                    }
+                }
+                unsigned todo = __ballot_sync(FULL, need_setup && active && (!is_done || auto_reset));
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const long long e_env = __shfl_sync(FULL, i, src);
+                    const int e_done = __shfl_sync(FULL, (int)is_done, src);
+                    const uint32_t e_epi = __shfl_sync(FULL, episode, src) + (e_done ? 1u : 0u);
+                    const int e_idx = e_done ? 0 : __shfl_sync(FULL, index, src);
+                    if (kCurves) wind_setup_warp(c, e_env, e_epi, e_idx, scratch);
+                    if (lane == src) {
+                        if (kCurves) {
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) {
+                                wa[m] = (T)scratch[kCoefDoubles + m];
+                                wb[m] = (T)scratch[kCoefDoubles + 4 + m];
+                            }
+                            wind_dirty = true;
+                        }
+                        if (e_done) {  // Boat.__init__  boat_env.py:144-201
+#pragma unroll
+                            for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
+                            const T sy0 = (T)episode_start_y(c, i, e_epi);  // :166-167
+                            d[D_SY] = sy0;
+                            index = 0;
+                            episode = e_epi;
+                            stage_reset_obs<T>(c, row, sy0);
+                        }
+                    }
+                    __syncwarp();  // scratch is reused by the next env of this warp
+                }
             }
         }
-    }
 
-    // ---- store ----
-    const bool done = code != BOATENV_TERM_NONE;
-    if (active) {
-        store_group<T, D_COUNT>(c.dyn, c.n_envs, i, d);
-        __stcs(c.idx + i, make_uint2((uint32_t)index, episode));
-        if (wind_dirty) {  // wind coefficients change only on the slow path
-            if (kCurves) store_group<T, 4>(c.windA, c.n_envs, i, wa);
-            if (WK == WIND_BOTH) store_group<T, 4>(c.windB, c.n_envs, i, wb);
-        }
-        __stcs(reinterpret_cast<T *>(a.reward_out) + i, rsum);
-        a.done_out[i] = done ? 1 : 0;
-        if (a.term_out) a.term_out[i] = (uint8_t)code;
-        if (a.steps_out) a.steps_out[i] = nsteps;
-    }
-    __syncwarp();  // the warp's staging tile is complete
-    if (a.rp.state) {  // fused store_transition  buffer.py:13-22: ring slots of a warp are contiguous (mod size)
-        const unsigned skip = __ballot_sync(FULL, next_stored);
-        const T *prev = reinterpret_cast<const T *>(a.obs_in) + row0 * kObsDim;
-        T *ring_s = reinterpret_cast<T *>(a.rp.state), *ring_n = reinterpret_cast<T *>(a.rp.new_state);
-        for (int e = lane; e < rows * kObsDim; e += 32) {
-            const int rr = e / kObsDim, q = e - rr * kObsDim;
-            long long slot = a.rp.base_slot + row0 + rr;
-            if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
-            ring_s[slot * kObsDim + q] = prev[e];
-            if (!((skip >> rr) & 1u)) ring_n[slot * kObsDim + q] = tile[e];
-        }
+        // ---- store ----
+        const bool done = code != BOATENV_TERM_NONE;
+        char *gb = c.state + blk * (long long)bb;
         if (active) {
-            long long slot = a.rp.base_slot + i;
-            if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
-            reinterpret_cast<T *>(a.rp.action)[slot] = action;
-            reinterpret_cast<T *>(a.rp.reward)[slot] = rsum;
-            a.rp.terminal[slot] = a.rp.done_flag_mode ? (code == BOATENV_TERM_REACHED_GOAL) : done;
+            store_vecs<T, D_COUNT>(gb, lane, d);
+            __stcs(reinterpret_cast<uint2 *>(gb + c.off_idx) + lane, make_uint2((uint32_t)index, episode));
+            if (wind_dirty) {  // wind coefficients change only on the slow path
+                if (kCurves) store_vecs<T, 4>(gb + c.off_wa, lane, wa);
+                if (WK == WIND_BOTH) store_vecs<T, 4>(gb + c.off_wb, lane, wb);
+            }
+            __stcs(reinterpret_cast<T *>(a.reward_out) + i, rsum);
+            a.done_out[i] = done ? 1 : 0;
+            if (a.term_out) a.term_out[i] = (uint8_t)code;
+            if (a.steps_out) a.steps_out[i] = nsteps;
         }
-        __syncwarp();  // prev rows are read before the copy-out below overwrites them (obs_in may alias obs_out)
+        if (a.rp.state) {  // fused store_transition  buffer.py:13-22: ring slots of a warp are contiguous (mod size)
+            __syncwarp();  // the warp's staging tile is complete
+            const unsigned skip = __ballot_sync(FULL, next_stored);
+            const T *prev = reinterpret_cast<const T *>(a.obs_in) + row0 * kObsDim;
+            T *ring_s = reinterpret_cast<T *>(a.rp.state), *ring_n = reinterpret_cast<T *>(a.rp.new_state);
+            for (int e = lane; e < rows * kObsDim; e += 32) {
+                const int rr = e / kObsDim, q = e - rr * kObsDim;
+                long long slot = a.rp.base_slot + row0 + rr;
+                if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
+                ring_s[slot * kObsDim + q] = prev[e];
+                if (!((skip >> rr) & 1u)) ring_n[slot * kObsDim + q] = tile[e];
+            }
+            if (active) {
+                long long slot = a.rp.base_slot + i;
+                if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
+                reinterpret_cast<T *>(a.rp.action)[slot] = action;
+                reinterpret_cast<T *>(a.rp.reward)[slot] = rsum;
+                a.rp.terminal[slot] = a.rp.done_flag_mode ? (code == BOATENV_TERM_REACHED_GOAL) : done;
+            }
+            // prev rows are read before the copy-out below overwrites them (obs_in may alias obs_out)
+        }
+        // ---- observations: the [rows][11] tile is contiguous in obs_out -> one bulk store ----
+        T *gobs = reinterpret_cast<T *>(a.obs_out) + row0 * kObsDim;
+        if (rows == 32) {
+            fence_proxy_async_smem();  // each lane: its st.shared rows -> visible to the async proxy
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_1d(gobs, tile, kTileBytes);
+                tma_store_commit();
+            }
+            tile_in_flight = true;
+        } else {
+            __syncwarp();
+            for (int e = lane; e < rows * kObsDim; e += 32) gobs[e] = tile[e];
+        }
     }
-    copy_out_tile<T>(tile, reinterpret_cast<T *>(a.obs_out), row0, rows, lane);
+    if (tile_in_flight && lane == 0) tma_store_wait_all();  // smem must stay valid until the last store has read it
 }
 
 }  // namespace boatenv

@@ -1,9 +1,13 @@
 // common.cuh -- shared host/device definitions of libboatenv (sm_100a).
 //
-// State layout in HBM (DESIGN.md "data layout"): structure-of-arrays of 16-byte
-// vectors.  Scalar k of env i of a group lives in vector k / VW (VW = 16/sizeof(T)),
-// slot k % VW, at  base + (vector * n_envs + i) * 16 bytes, so that a warp's access to
-// one vector is one fully coalesced 512-byte LDG.128 / STG.128.
+// State layout in HBM (DESIGN.md "data layout"): tile-blocked structure-of-arrays.  The
+// carried state of 32 consecutive envs (one warp's tile) is ONE contiguous, 16-byte
+// aligned block
+//     [dyn vector 0 x 32][dyn vector 1 x 32]..[idx (uint2) x 32][wind A vectors x 32][wind B vectors x 32]
+// of 16-byte vectors (VW = 16/sizeof(T) scalars each), so that
+//   * the whole block is fetched by a single TMA bulk copy (cp.async.bulk) into shared memory,
+//   * a warp's access to one vector row is one fully coalesced 512-byte LDS/LDG/STG.128.
+// Block size: 32 * (16*ND + 8 + 16*NW*ncurves) bytes = 1280 / 1792 / 2304 (fp32; exp 1-3 / 4-5 / 6).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -65,9 +69,9 @@ struct DevCfg {
     double prop_d4;           // np.power(propeller_diameter, 4)  boat_env.py:226
     FastConsts f;
     // device buffers (owned by the handle)
-    void *dyn;                // D_COUNT scalars per env, vectorised (see top of file)
-    void *windA, *windB;      // 4 cubic coefficients per env per random curve
-    uint2 *idx;               // (step index, episode index) per env
+    char *state;              // [ceil(n_envs / 32)][block_bytes] tile-blocked state (see top of file)
+    int block_bytes;          // bytes of one 32-env block
+    int off_idx, off_wa, off_wb;  // byte offsets of the idx / wind A / wind B sections inside a block
     const double *basis;      // [npieces][4][fp] cardinal not-a-knot spline basis
     double *counters;         // [kCounterSlots][kNumCounters]
     const int32_t *ovr_s_y;   // optional episode-draw overrides (validation)
@@ -176,21 +180,49 @@ __device__ __forceinline__ void unpack(const double2 &v, double *o) { o[0] = v.x
 __device__ __forceinline__ float4 pack(const float *o) { return make_float4(o[0], o[1], o[2], o[3]); }
 __device__ __forceinline__ double2 pack(const double *o) { return make_double2(o[0], o[1]); }
 
-// NS scalars of env i: NS / VW streaming 128-bit loads (evict-first: every byte of
-// state is touched exactly once per step, nothing is worth keeping in L1/L2).
+// Vectors per env of the two section kinds.
+template <typename T> struct Lay {
+    static constexpr int ND = D_COUNT * (int)sizeof(T) / 16;  // dyn: 8 scalars
+    static constexpr int NW = 4 * (int)sizeof(T) / 16;        // one wind curve: 4 cubic coefficients
+};
+
+__host__ __device__ __forceinline__ long long num_blocks(long long n_envs) { return (n_envs + 31) >> 5; }
+
+// Section `off` of the block that holds env i (global memory).
+__device__ __forceinline__ char *block_section(const DevCfg &c, long long i, int off) {
+    return c.state + (i >> 5) * (long long)c.block_bytes + off;
+}
+
+// NS scalars of lane `lane` from a section (vector row v at sec + (v*32 + lane)*16).
+template <typename T, int NS>
+__device__ __forceinline__ void load_vecs(const char *sec, int lane, T (&out)[NS]) {
+    using V = typename VecOf<T>::type;
+    constexpr int W = VecOf<T>::W;
+    static_assert(NS % W == 0, "section must be a whole number of 16-byte vectors");
+    const V *p = reinterpret_cast<const V *>(sec) + lane;
+#pragma unroll
+    for (int v = 0; v < NS / W; ++v) unpack(p[v * 32], &out[v * W]);
+}
+
+// Streaming (evict-first) 128-bit stores of NS scalars: every byte of state is written once per step.
+template <typename T, int NS>
+__device__ __forceinline__ void store_vecs(char *sec, int lane, const T (&in)[NS]) {
+    using V = typename VecOf<T>::type;
+    constexpr int W = VecOf<T>::W;
+    V *p = reinterpret_cast<V *>(sec) + lane;
+#pragma unroll
+    for (int v = 0; v < NS / W; ++v) __stcs(p + v * 32, pack(&in[v * W]));
+}
+
+// Plain per-array SoA helpers (toy envs: 4 scalars per env in [vector][env] order).
 template <typename T, int NS>
 __device__ __forceinline__ void load_group(const void *base, long long n, long long i, T (&out)[NS]) {
     using V = typename VecOf<T>::type;
     constexpr int W = VecOf<T>::W;
-    static_assert(NS % W == 0, "group must be a whole number of 16-byte vectors");
     const V *p = reinterpret_cast<const V *>(base);
 #pragma unroll
-    for (int v = 0; v < NS / W; ++v) {
-        V x = __ldcs(p + (long long)v * n + i);
-        unpack(x, &out[v * W]);
-    }
+    for (int v = 0; v < NS / W; ++v) unpack(__ldcs(p + (long long)v * n + i), &out[v * W]);
 }
-
 template <typename T, int NS>
 __device__ __forceinline__ void store_group(void *base, long long n, long long i, const T (&in)[NS]) {
     using V = typename VecOf<T>::type;

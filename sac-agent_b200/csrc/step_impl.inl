@@ -11,20 +11,48 @@ namespace boatenv {
 
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
+// Persistent launch: enough CTAs to fill every SM at the kernel's occupancy (queried once per
+// instantiation and shared-memory size), never more than there are 8-warp groups of blocks.
+template <int WK>
+static cudaError_t launch_step_wk(const DevCfg &c, const StepArgs &a, cudaStream_t st) {
+    auto kern = boat_step_kernel<REAL, WK>;
+    const int smem = kWarpsPerCta * warp_smem_bytes<REAL>(c.block_bytes);
+    static int cached_smem = -1, ctas_per_sm = 0, n_sm = 0, cached_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cached_smem != smem || cached_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kTile, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
+        cached_smem = smem;
+        cached_dev = dev;
+    }
+    const long long nblk = ((a.env_end + 31) >> 5) - (a.env_begin >> 5);
+    long long grid = (nblk + kWarpsPerCta - 1) / kWarpsPerCta;
+    const long long resident = (long long)n_sm * ctas_per_sm;
+    if (grid > resident) grid = resident;
+    kern<<<(unsigned)grid, kTile, smem, st>>>(c, a);
+    return cudaGetLastError();
+}
+
 cudaError_t FN(launch_step_)(const DevCfg &c, const StepArgs &a, cudaStream_t st) {
-    const long long n = a.env_end - a.env_begin;
-    if (n <= 0) return cudaSuccess;
-    const dim3 grid(grid_for(n, kTile)), block(kTile);
+    if (a.env_end <= a.env_begin) return cudaSuccess;
+    if (a.env_begin & 31) return cudaErrorInvalidValue;  // launches start on a state-block boundary
+    cudaError_t e;
     switch (c.wind_kind) {
-    case WIND_NONE: boat_step_kernel<REAL, WIND_NONE><<<grid, block, 0, st>>>(c, a); break;
-    case WIND_CONST: boat_step_kernel<REAL, WIND_CONST><<<grid, block, 0, st>>>(c, a); break;
-    case WIND_VEL_CURVE: boat_step_kernel<REAL, WIND_VEL_CURVE><<<grid, block, 0, st>>>(c, a); break;
-    case WIND_ANGLE_RECT: boat_step_kernel<REAL, WIND_ANGLE_RECT><<<grid, block, 0, st>>>(c, a); break;
-    case WIND_BOTH: boat_step_kernel<REAL, WIND_BOTH><<<grid, block, 0, st>>>(c, a); break;
+    case WIND_NONE: e = launch_step_wk<WIND_NONE>(c, a, st); break;
+    case WIND_CONST: e = launch_step_wk<WIND_CONST>(c, a, st); break;
+    case WIND_VEL_CURVE: e = launch_step_wk<WIND_VEL_CURVE>(c, a, st); break;
+    case WIND_ANGLE_RECT: e = launch_step_wk<WIND_ANGLE_RECT>(c, a, st); break;
+    case WIND_BOTH: e = launch_step_wk<WIND_BOTH>(c, a, st); break;
     default: return cudaErrorInvalidValue;
     }
     count_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 cudaError_t FN(launch_reset_)(const DevCfg &c, const uint8_t *mask, void *obs_out, cudaStream_t st) {
