@@ -236,7 +236,7 @@ def run_ours(args) -> None:
     stats = torch.zeros(8, dtype=torch.float64, device=dev)
 
     def one_step(t, ev=None):
-        env.uniform_actions(t, 1.0, out=actions)       # the policy (1 launch)
+        env.uniform_actions(t, args.action_scale, out=actions)       # the policy (1 launch)
         if ev is not None:
             ev[0].record()
         env.step(actions)                               # BoatEnv.step for every env (1 launch)
@@ -348,6 +348,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-timed part only (for ncu runs)")
+    ap.add_argument("--action-scale", type=float, default=1.0, help="experiments only: scale of the uniform policy")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -145,6 +145,10 @@ static int derive_config(const boatenv_params *p, DevCfg &c) {
         while (n < c.L + 16) { t += p->dt; ++n; if (p->t_max <= t) break; }
         c.timeout_steps = n;
     }
+    {   // boat_env.py:70,94: fuel starts at p->fuel, loses 1 per step, out_of_fuel when fuel < 0
+        const double fs = std::floor(p->fuel) + 1.0;
+        c.fuel_steps = fs < 1.0 ? 1 : (fs > 2147483647.0 ? 2147483647 : (int)fs);
+    }
     c.s_y_half = (int)(p->track_width * 0.8);  // boat_env.py:148-149
     if (c.s_y_half < 1) c.s_y_half = 1;
     c.direction_rad = p->direction * (PI / 180.0);
@@ -233,6 +237,7 @@ int boatenv_create(const boatenv_params *params, int64_t n_envs, uint64_t seed, 
                    int precision, int device, boatenv_t *out) {
     if (!params || !out || n_envs <= 0 || env_id_offset < 0) return BOATENV_EINVAL;
     if (precision != 32 && precision != 64) return BOATENV_EINVAL;
+    if (n_envs > 2147483647LL - 64) return BOATENV_EUNSUPPORTED;  // per-handle env indices are 32-bit in the kernels
     *out = nullptr;
     DevCfg cfg;
     int rc = derive_config(params, cfg);

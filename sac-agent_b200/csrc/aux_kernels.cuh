@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(kTile) boat_reset_kernel(const __grid_constant
             d[D_SY] = sy0;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-                wa[m] = c.ncurves > 0 ? (T)scratch_s[warp][kCoefDoubles + m] : (T)0;
-                wb[m] = c.ncurves > 0 ? (T)scratch_s[warp][kCoefDoubles + 4 + m] : (T)0;
+                wa[m] = c.ncurves > 0 ? (T)scratch_s[warp][m] : (T)0;
+                wb[m] = c.ncurves > 0 ? (T)scratch_s[warp][4 + m] : (T)0;
             }
             store_vecs<T, D_COUNT>(block_section(c, i, 0), lane, d);
             reinterpret_cast<uint2 *>(block_section(c, i, c.off_idx))[lane] = make_uint2(0u, e_epi);
@@ -64,7 +64,7 @@ static __global__ void __launch_bounds__(32) boat_wind_table_kernel(const __grid
         for (int j = 0; j < c.npieces; ++j) {
             const int first_index = (j * c.Lm1 + c.npieces - 1) / c.npieces;
             wind_setup_warp(c, env, episode, first_index, scratch_s);
-            if (lane < 8) folded[j][lane] = scratch_s[kCoefDoubles + lane];
+            if (lane < 8) folded[j][lane] = scratch_s[lane];
             __syncwarp();
         }
     }

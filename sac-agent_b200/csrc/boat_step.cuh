@@ -10,31 +10,42 @@
 namespace boatenv {
 
 // ---------------------------------------------------------------------------------
-// fp32 transcendental helpers: Cody-Waite reduction by pi/2 + cephes-style minimax
-// polynomials on [-pi/4, pi/4]; |error| ~1e-7 for |x| up to ~1e4, no slow path.
+// fp32 transcendental helpers: Cody-Waite reduction by pi (k = rint(x/pi), r = x - k*pi in
+// [-pi/2, pi/2], sin x = (-1)^k sin r, cos x = (-1)^k cos r) + near-minimax polynomials
+// (odd degree 9 / even degree 10, fitted on [-pi/2, pi/2]); |error| ~1.3e-7 for |x| up to
+// ~1e4, branch-free, no slow path.  13 instructions for sin, 18 for sin+cos.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void fast_sincosf(float x, float &s, float &c) {
-    float k = fmaf(x, 0.636619747f, 12582912.0f);
-    const int q = __float_as_int(k);
+__device__ __forceinline__ float reduce_pi(float x, uint32_t &sign) {
+    float k = fmaf(x, 0.318309886f, 12582912.0f);
+    sign = (uint32_t)__float_as_int(k) << 31;     // parity of k -> sign bit
     k -= 12582912.0f;
-    float r = fmaf(k, -1.57079637e+00f, x);   // fl32(pi/2)
-    r = fmaf(k, 4.37113883e-08f, r);          // pi/2 - fl32(pi/2) = -4.371e-8
-    const float r2 = r * r;
-    float sp = fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f);
-    sp = fmaf(sp, r2, -1.6666654611e-1f);
-    sp = fmaf(sp * r2, r, r);
-    float cp = fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f);
-    cp = fmaf(cp, r2, 4.166664568298827e-2f);
-    cp = fmaf(cp * r2, r2, fmaf(-0.5f, r2, 1.0f));
-    const float ss = (q & 1) ? cp : sp;
-    const float cc = (q & 1) ? sp : cp;
-    s = (q & 2) ? -ss : ss;
-    c = ((q + 1) & 2) ? -cc : cc;
+    float r = fmaf(k, -3.14159274e+00f, x);       // fl32(pi)
+    return fmaf(k, 8.74227766e-08f, r);           // fl32(pi) - pi = 8.742e-8
+}
+__device__ __forceinline__ float sin_poly(float r, float r2) {
+    float p = fmaf(2.5904564607e-06f, r2, -1.9800881965e-04f);
+    p = fmaf(p, r2, 8.3328995679e-03f);
+    p = fmaf(p, r2, -1.6666647620e-01f);
+    return fmaf(r2 * r, p, r);
+}
+__device__ __forceinline__ float cos_poly(float r2) {
+    float q = fmaf(-2.6051228305e-07f, r2, 2.4760146865e-05f);
+    q = fmaf(q, r2, -1.3888361132e-03f);
+    q = fmaf(q, r2, 4.1666636239e-02f);
+    q = fmaf(q, r2, -4.9999999358e-01f);
+    return fmaf(q, r2, 1.0f);
 }
 __device__ __forceinline__ float fast_sinf(float x) {
-    float s, c;
-    fast_sincosf(x, s, c);
-    return s;
+    uint32_t sign;
+    const float r = reduce_pi(x, sign);
+    return __uint_as_float(__float_as_uint(sin_poly(r, r * r)) ^ sign);
+}
+__device__ __forceinline__ void fast_sincosf(float x, float &s, float &c) {
+    uint32_t sign;
+    const float r = reduce_pi(x, sign);
+    const float r2 = r * r;
+    s = __uint_as_float(__float_as_uint(sin_poly(r, r2)) ^ sign);
+    c = __uint_as_float(__float_as_uint(cos_poly(r2)) ^ sign);
 }
 
 // ---------------------------------------------------------------------------------
@@ -162,17 +173,18 @@ __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], in
     fast_sincosf(s_r, sr, cr);
     const float s_x = fmaf(fmaf(v_x, cr, -v_y * sr), f.dt, d[D_SX]);
     const float s_y = fmaf(fmaf(v_y, cr, v_x * sr), f.dt, d[D_SY]);
-    const float fuel = f.fuel0 - (float)(index + 1);
-
     const float ay = fabsf(s_y);
     float r = -__fdividef(ay * f.rew_inv_W, 1.0f + __expf(f.rew_k * (ay - f.rew_y0)));
-    code = BOATENV_TERM_NONE;
+    // termination cascade boat_env.py:84-105, lowest priority first (later selects override);
+    // fuel < 0 (:94) and t_max <= t (:98) depend on the step count only: integer thresholds
     const float ar = fabsf(rudder);
-    if (s_x >= f.goal) { code = BOATENV_TERM_REACHED_GOAL; r += 1000.0f; }
-    else if (ay > f.oob || s_x < 0.0f) code = BOATENV_TERM_OUT_OF_BOUNDS;
-    else if (fuel < 0.0f) code = BOATENV_TERM_OUT_OF_FUEL;
-    else if (index + 1 >= c.timeout_steps) code = BOATENV_TERM_TIMEOUT;
-    else if (ar > f.pi3) code = BOATENV_TERM_RUDDER_BROKEN;
+    const bool goal = s_x >= f.goal;
+    code = (ar > f.pi3) ? BOATENV_TERM_RUDDER_BROKEN : BOATENV_TERM_NONE;
+    code = (index + 1 >= c.timeout_steps) ? BOATENV_TERM_TIMEOUT : code;
+    code = (index + 1 >= c.fuel_steps) ? BOATENV_TERM_OUT_OF_FUEL : code;
+    code = (ay > f.oob || s_x < 0.0f) ? BOATENV_TERM_OUT_OF_BOUNDS : code;
+    code = goal ? BOATENV_TERM_REACHED_GOAL : code;
+    r += goal ? 1000.0f : 0.0f;
     if (ar > f.pi4) r = fmaf(-100.0f, ar, r);
     if (fabsf(s_r) > f.pi2) r -= 1.0f;
     reward = r;
@@ -277,9 +289,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // global -> shared bulk copy, completion counted in bytes on `bar`; L2 evict-first (streamed once)
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar,
                                             uint64_t policy) {
+#ifdef BOAT_NO_L2HINT
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                     "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+#else
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
             "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+#endif
 }
 // shared -> global bulk copy (bulk async-group completion)
 __device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
@@ -312,9 +329,15 @@ constexpr int kStages = BOAT_STAGES;
 // Shared memory of one warp (dynamic smem, carved per warp): the TMA stages, the observation
 // staging tile, the slow-path scratch and the stage barriers.
 template <typename T>
-__host__ __device__ constexpr int warp_smem_bytes(int block_bytes) {
-    return (kStages * block_bytes + 32 * kObsDim * (int)sizeof(T) + kScratchDoubles * 8 + kStages * 8 + 127) / 128 * 128;
-}
+struct WarpSmem {
+    int tile_off, scratch_off, bar_off, bytes;
+    __host__ __device__ WarpSmem(int block_bytes, int ncurves, int npieces) {
+        tile_off = kStages * block_bytes;
+        scratch_off = tile_off + 32 * kObsDim * (int)sizeof(T);
+        bar_off = scratch_off + scratch_doubles(ncurves, npieces) * 8;
+        bytes = (bar_off + kStages * 8 + 127) / 128 * 128;
+    }
+};
 
 // Persistent kernel, one thread per env, every warp self-contained: warp w walks the 32-env
 // state blocks w, w + W, w + 2W, ... (W = warps in the grid).  Its lane 0 keeps kStages TMA
@@ -322,7 +345,11 @@ __host__ __device__ constexpr int warp_smem_bytes(int block_bytes) {
 // by the pipeline instead of by occupancy; lanes read their state from shared memory, run the
 // K sub-steps in registers, write the state back with coalesced 128-bit stores and the
 // [32][11] observation tile with one bulk store.  No CTA-wide barrier anywhere.
-template <typename T, int WK>
+//
+// KMULTI = false is the gym-faithful one-sub-step-per-launch instantiation: the state is
+// written back right after the sub-step and the (rare) slow path patches the affected envs
+// in global memory, so that almost nothing is live in registers across the slow path.
+template <typename T, int WK, bool KMULTI>
 __global__ void __launch_bounds__(kTile, StepTuning<T>::kMinBlocks)
 boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -332,16 +359,18 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bb = c.block_bytes;
 
-    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<T>(bb);
+    const WarpSmem<T> lay(bb, c.ncurves, c.npieces);
+    unsigned char *wbase = smem_raw + (size_t)warp * lay.bytes;
     unsigned char *stage_base = wbase;                                  // kStages * bb   (16-byte aligned)
-    T *tile = reinterpret_cast<T *>(wbase + kStages * bb);              // [32][11]
-    double *scratch = reinterpret_cast<double *>(wbase + kStages * bb + kTileBytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(wbase + kStages * bb + kTileBytes + kScratchDoubles * 8);
+    T *tile = reinterpret_cast<T *>(wbase + lay.tile_off);              // [32][11]
+    double *scratch = reinterpret_cast<double *>(wbase + lay.scratch_off);
+    uint64_t *full = reinterpret_cast<uint64_t *>(wbase + lay.bar_off);
     T *row = tile + lane * kObsDim;
 
-    const long long blk_begin = a.env_begin >> 5, blk_end = (a.env_end + 31) >> 5;
-    const long long wstride = (long long)gridDim.x * kWarpsPerCta;
-    long long blk = blk_begin + (long long)blockIdx.x * kWarpsPerCta + warp;
+    // env indices of one handle fit 32 bits (checked at create)
+    const int n_end = (int)a.env_end, blk_end = (n_end + 31) >> 5;
+    const int wstride = (int)gridDim.x * kWarpsPerCta;
+    int blk = (int)(a.env_begin >> 5) + (int)blockIdx.x * kWarpsPerCta + warp;
     if (blk >= blk_end) return;
 
     const uint64_t pol = policy_evict_first();
@@ -354,28 +383,27 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
     if (lane == 0) {  // prologue: fill the pipeline
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
-            const long long b = blk + s * wstride;
+            const int b = blk + s * wstride;
             if (b < blk_end) {
                 mbar_expect_tx(full + s, (uint32_t)bb);
-                tma_load_1d(stage_base + s * bb, c.state + b * (long long)bb, (uint32_t)bb, full + s, pol);
+                tma_load_1d(stage_base + s * bb, c.state + (size_t)b * (size_t)bb, (uint32_t)bb, full + s, pol);
             }
         }
     }
     const T *act = reinterpret_cast<const T *>(a.actions);
     const T inv_Lm1 = sizeof(T) == 8 ? (T)c.inv_Lm1 : (T)c.f.inv_Lm1;
     const bool auto_reset = (a.flags & BOATENV_AUTO_RESET) != 0;
-    T action_next = __ldcs(act + min(blk * 32 + lane, a.env_end - 1));
+    const int ksteps = KMULTI ? a.ksteps : 1;
+    T action_next = __ldcs(act + min(blk * 32 + lane, n_end - 1));
     int stage = 0;
     uint32_t parity = 0;
     bool tile_in_flight = false;  // a bulk store of `tile` may still be reading it
 
     for (; blk < blk_end; blk += wstride) {
-        const long long row0 = blk * 32;
-        const long long i = row0 + lane;
-        const bool active = i < a.env_end;  // inactive lanes are the padding of the last block (no stores)
-        const int rows = (int)min(32LL, a.env_end - row0);
+        const int i = blk * 32 + lane;
+        const bool active = i < n_end;  // inactive lanes are the padding of the last block (no stores)
         T action = action_next;
-        if (blk + wstride < blk_end) action_next = __ldcs(act + min((blk + wstride) * 32 + lane, a.env_end - 1));
+        if (blk + wstride < blk_end) action_next = __ldcs(act + min(i + wstride * 32, n_end - 1));
 
         // ---- state: wait for the TMA copy of this block, read it from shared memory ----
         const unsigned char *sb = stage_base + stage * bb;
@@ -393,10 +421,10 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             // The stage is consumed: refill it kStages blocks ahead.  The block number carries a data
             // dependency on the LAST shared-memory load of the stage (bit 31 of the step index is never
             // set), so the bulk copy cannot be issued before the warp's loads have returned.
-            const long long b = blk + (long long)kStages * wstride + (long long)(ix.x >> 31);
+            const int b = blk + kStages * wstride + (int)(ix.x >> 31);
             if (b < blk_end) {
                 mbar_expect_tx(full + stage, (uint32_t)bb);
-                tma_load_1d(stage_base + stage * bb, c.state + b * (long long)bb, (uint32_t)bb, full + stage, pol);
+                tma_load_1d(stage_base + stage * bb, c.state + (size_t)b * (size_t)bb, (uint32_t)bb, full + stage, pol);
             }
         }
         if (++stage == kStages) { stage = 0; parity ^= 1u; }
@@ -409,9 +437,30 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             __syncwarp();
             tile_in_flight = false;
         }
+        char *gb = c.state + (size_t)blk * (size_t)bb;
 
-        for (int k = 0; k < a.ksteps; ++k) {
-            if (k > 0 && a.action_stride != 0) action = __ldcs(act + (long long)k * a.action_stride + min(i, a.env_end - 1));
+        // state + per-env outputs of this launch (K = 1: right after the sub-step; K > 1: after the loop)
+        auto store_results = [&]() {
+            if (active) {
+                store_vecs<T, D_COUNT>(gb, lane, d);
+                __stcs(reinterpret_cast<uint2 *>(gb + c.off_idx) + lane, make_uint2((uint32_t)index, episode));
+                if (KMULTI && wind_dirty) {  // wind coefficients change only on the slow path
+                    if (kCurves) store_vecs<T, 4>(gb + c.off_wa, lane, wa);
+                    if (WK == WIND_BOTH) store_vecs<T, 4>(gb + c.off_wb, lane, wb);
+                }
+                __stcs(reinterpret_cast<T *>(a.reward_out) + i, rsum);
+                a.done_out[i] = (code != BOATENV_TERM_NONE) ? 1 : 0;
+                if (a.term_out) a.term_out[i] = (uint8_t)code;
+                if (KMULTI) {
+                    if (a.steps_out) a.steps_out[i] = nsteps;
+                }
+            }
+        };
+
+        for (int k = 0; k < ksteps; ++k) {
+            if (KMULTI) {
+                if (k > 0 && a.action_stride != 0) action = __ldcs(act + (size_t)k * (size_t)a.action_stride + min(i, n_end - 1));
+            }
             bool need_setup = false;
             if (alive) {
                 // ---- wind sample wind[index] from the carried piece coefficients ----
@@ -437,11 +486,15 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                 if (WK == WIND_CONST) { w = (T)c.p.max_velocity; th = (T)c.direction_rad; }
 
                 T rew, acc[3];
+#ifdef BOAT_DEBUG_NOCOMPUTE  // memory-pattern experiment only: stream the state through untouched
+                acc[0] = acc[1] = acc[2] = w + th; rew = action; code = BOATENV_TERM_NONE;
+#else
                 substep<WK>(c, d, index, action, w, th, acc, rew, code);
+#endif
                 rsum += rew;
                 ++nsteps;
                 index += 1;
-                if (code != BOATENV_TERM_NONE || k == a.ksteps - 1) stage_obs(c, row, d, acc, index);
+                if (code != BOATENV_TERM_NONE || k == ksteps - 1) stage_obs(c, row, d, acc, index);
                 if (code != BOATENV_TERM_NONE) {
                     alive = false;
                     need_setup = true;  // statistics, and the reset if AUTO_RESET
@@ -450,12 +503,13 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                     if (r + c.npieces >= c.Lm1 && j + 1 <= c.npieces - 1) need_setup = true;
                 }
             }
+            if (!KMULTI) store_results();
             // ---- slow path: the warp serves its lanes one at a time ----
             if (__ballot_sync(FULL, need_setup && active)) {
                 const bool is_done = need_setup && active && code != BOATENV_TERM_NONE;
                 const unsigned dmask = __ballot_sync(FULL, is_done);
                 if (dmask) {  // statistics (info dict, boat_env.py:24-32,87-113): one atomic per counter per warp
-                    double *cnt = c.counters + (int)(blk % kCounterSlots) * 32;
+                    double *cnt = c.counters + (blk & (kCounterSlots - 1)) * 32;
 #pragma unroll
                     for (int t = 1; t <= 5; ++t) {
                         const unsigned m = __ballot_sync(FULL, is_done && code == t);
@@ -471,7 +525,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                 }
                 if (is_done) {  // the terminal observation leaves before a reset overwrites the row
                     if (a.final_obs_out) {
-                        T *fo = reinterpret_cast<T *>(a.final_obs_out) + i * kObsDim;
+                        T *fo = reinterpret_cast<T *>(a.final_obs_out) + (size_t)i * kObsDim;
 #pragma unroll
                         for (int q = 0; q < kObsDim; ++q) fo[q] = row[q];
                     }
@@ -488,19 +542,22 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                 while (todo) {
                     const int src = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    const long long e_env = __shfl_sync(FULL, i, src);
                     const int e_done = __shfl_sync(FULL, (int)is_done, src);
                     const uint32_t e_epi = __shfl_sync(FULL, episode, src) + (e_done ? 1u : 0u);
                     const int e_idx = e_done ? 0 : __shfl_sync(FULL, index, src);
-                    if (kCurves) wind_setup_warp(c, e_env, e_epi, e_idx, scratch);
+                    if (kCurves) wind_setup_warp(c, (long long)(blk * 32 + src), e_epi, e_idx, scratch);
                     if (lane == src) {
                         if (kCurves) {
 #pragma unroll
                             for (int m = 0; m < 4; ++m) {
-                                wa[m] = (T)scratch[kCoefDoubles + m];
-                                wb[m] = (T)scratch[kCoefDoubles + 4 + m];
+                                wa[m] = (T)scratch[m];
+                                wb[m] = (T)scratch[4 + m];
                             }
                             wind_dirty = true;
+                            if (!KMULTI) {  // patch the block in global memory
+                                store_vecs<T, 4>(gb + c.off_wa, lane, wa);
+                                if (WK == WIND_BOTH) store_vecs<T, 4>(gb + c.off_wb, lane, wb);
+                            }
                         }
                         if (e_done) {  // Boat.__init__  boat_env.py:144-201
 #pragma unroll
@@ -510,36 +567,27 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                             index = 0;
                             episode = e_epi;
                             stage_reset_obs<T>(c, row, sy0);
+                            if (!KMULTI) {
+                                store_vecs<T, D_COUNT>(gb, lane, d);
+                                __stcs(reinterpret_cast<uint2 *>(gb + c.off_idx) + lane, make_uint2(0u, e_epi));
+                            }
                         }
                     }
                     __syncwarp();  // scratch is reused by the next env of this warp
                 }
             }
         }
+        if (KMULTI) store_results();
 
-        // ---- store ----
-        const bool done = code != BOATENV_TERM_NONE;
-        char *gb = c.state + blk * (long long)bb;
-        if (active) {
-            store_vecs<T, D_COUNT>(gb, lane, d);
-            __stcs(reinterpret_cast<uint2 *>(gb + c.off_idx) + lane, make_uint2((uint32_t)index, episode));
-            if (wind_dirty) {  // wind coefficients change only on the slow path
-                if (kCurves) store_vecs<T, 4>(gb + c.off_wa, lane, wa);
-                if (WK == WIND_BOTH) store_vecs<T, 4>(gb + c.off_wb, lane, wb);
-            }
-            __stcs(reinterpret_cast<T *>(a.reward_out) + i, rsum);
-            a.done_out[i] = done ? 1 : 0;
-            if (a.term_out) a.term_out[i] = (uint8_t)code;
-            if (a.steps_out) a.steps_out[i] = nsteps;
-        }
+        const int rows = min(32, n_end - blk * 32);
         if (a.rp.state) {  // fused store_transition  buffer.py:13-22: ring slots of a warp are contiguous (mod size)
             __syncwarp();  // the warp's staging tile is complete
             const unsigned skip = __ballot_sync(FULL, next_stored);
-            const T *prev = reinterpret_cast<const T *>(a.obs_in) + row0 * kObsDim;
+            const T *prev = reinterpret_cast<const T *>(a.obs_in) + (size_t)blk * (32 * kObsDim);
             T *ring_s = reinterpret_cast<T *>(a.rp.state), *ring_n = reinterpret_cast<T *>(a.rp.new_state);
             for (int e = lane; e < rows * kObsDim; e += 32) {
                 const int rr = e / kObsDim, q = e - rr * kObsDim;
-                long long slot = a.rp.base_slot + row0 + rr;
+                long long slot = a.rp.base_slot + blk * 32 + rr;
                 if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
                 ring_s[slot * kObsDim + q] = prev[e];
                 if (!((skip >> rr) & 1u)) ring_n[slot * kObsDim + q] = tile[e];
@@ -549,12 +597,12 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                 if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
                 reinterpret_cast<T *>(a.rp.action)[slot] = action;
                 reinterpret_cast<T *>(a.rp.reward)[slot] = rsum;
-                a.rp.terminal[slot] = a.rp.done_flag_mode ? (code == BOATENV_TERM_REACHED_GOAL) : done;
+                a.rp.terminal[slot] = a.rp.done_flag_mode ? (code == BOATENV_TERM_REACHED_GOAL) : (code != BOATENV_TERM_NONE);
             }
             // prev rows are read before the copy-out below overwrites them (obs_in may alias obs_out)
         }
         // ---- observations: the [rows][11] tile is contiguous in obs_out -> one bulk store ----
-        T *gobs = reinterpret_cast<T *>(a.obs_out) + row0 * kObsDim;
+        T *gobs = reinterpret_cast<T *>(a.obs_out) + (size_t)blk * (32 * kObsDim);
         if (rows == 32) {
             fence_proxy_async_smem();  // each lane: its st.shared rows -> visible to the async proxy
             __syncwarp();

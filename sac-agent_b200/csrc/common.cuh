@@ -63,6 +63,7 @@ struct DevCfg {
     unsigned magic_m, magic_s;  // floor(n / Lm1) == __umulhi(n, magic_m) >> magic_s for n <= L * npieces
     double inv_Lm1;           // 1.0 / Lm1
     int timeout_steps;        // first step count n with accumulated t >= t_max (boat_env.py:98)
+    int fuel_steps;           // first step count n with fuel - n < 0 (boat_env.py:70,94)
     int s_y_half;             // int(track_width * 0.8) (boat_env.py:148-149)
     boatenv_params p;         // raw reference parameters (fp64 validation mode uses these)
     double direction_rad;     // float(direction) * (pi/180)   wind.py:44

@@ -13,10 +13,10 @@ static inline unsigned grid_for(long long n, int block) { return (unsigned)((n +
 
 // Persistent launch: enough CTAs to fill every SM at the kernel's occupancy (queried once per
 // instantiation and shared-memory size), never more than there are 8-warp groups of blocks.
-template <int WK>
+template <int WK, bool KMULTI>
 static cudaError_t launch_step_wk(const DevCfg &c, const StepArgs &a, cudaStream_t st) {
-    auto kern = boat_step_kernel<REAL, WK>;
-    const int smem = kWarpsPerCta * warp_smem_bytes<REAL>(c.block_bytes);
+    auto kern = boat_step_kernel<REAL, WK, KMULTI>;
+    const int smem = kWarpsPerCta * WarpSmem<REAL>(c.block_bytes, c.ncurves, c.npieces).bytes;
     static int cached_smem = -1, ctas_per_sm = 0, n_sm = 0, cached_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -39,16 +39,21 @@ static cudaError_t launch_step_wk(const DevCfg &c, const StepArgs &a, cudaStream
     return cudaGetLastError();
 }
 
+template <int WK>
+static cudaError_t launch_step_k(const DevCfg &c, const StepArgs &a, cudaStream_t st) {
+    return a.ksteps == 1 ? launch_step_wk<WK, false>(c, a, st) : launch_step_wk<WK, true>(c, a, st);
+}
+
 cudaError_t FN(launch_step_)(const DevCfg &c, const StepArgs &a, cudaStream_t st) {
     if (a.env_end <= a.env_begin) return cudaSuccess;
     if (a.env_begin & 31) return cudaErrorInvalidValue;  // launches start on a state-block boundary
     cudaError_t e;
     switch (c.wind_kind) {
-    case WIND_NONE: e = launch_step_wk<WIND_NONE>(c, a, st); break;
-    case WIND_CONST: e = launch_step_wk<WIND_CONST>(c, a, st); break;
-    case WIND_VEL_CURVE: e = launch_step_wk<WIND_VEL_CURVE>(c, a, st); break;
-    case WIND_ANGLE_RECT: e = launch_step_wk<WIND_ANGLE_RECT>(c, a, st); break;
-    case WIND_BOTH: e = launch_step_wk<WIND_BOTH>(c, a, st); break;
+    case WIND_NONE: e = launch_step_k<WIND_NONE>(c, a, st); break;
+    case WIND_CONST: e = launch_step_k<WIND_CONST>(c, a, st); break;
+    case WIND_VEL_CURVE: e = launch_step_k<WIND_VEL_CURVE>(c, a, st); break;
+    case WIND_ANGLE_RECT: e = launch_step_k<WIND_ANGLE_RECT>(c, a, st); break;
+    case WIND_BOTH: e = launch_step_k<WIND_BOTH>(c, a, st); break;
     default: return cudaErrorInvalidValue;
     }
     count_launch();

@@ -19,8 +19,9 @@
 
 namespace boatenv {
 
-constexpr int kCoefDoubles = 2 * (kMaxKnots - 1) * 4;  // per warp: [curve][piece][4]
-constexpr int kScratchDoubles = kCoefDoubles + 8;      // + the folded result: a[4], b[4]
+// Per-warp scratch: [0..7] the folded result a[4], b[4]; [8..] the coefficient table [curve][piece][4].
+constexpr int kScratchDoubles = 8 + 2 * (kMaxKnots - 1) * 4;  // upper bound (static allocations)
+__host__ __device__ constexpr int scratch_doubles(int ncurves, int npieces) { return 8 + ncurves * npieces * 4; }
 
 // Piece index and local coordinate numerator of wind sample `index` (0 <= index < L):
 // x_index / h = index * (fp-1) / (L-1) exactly (x_index = index * L/(L-1), h = L/(fp-1)),
@@ -34,25 +35,26 @@ __device__ __forceinline__ void piece_of(const DevCfg &c, int index, int &j, int
     r = (int)(num - q * (uint32_t)c.Lm1);
 }
 
-__device__ __forceinline__ double eval_sample(const DevCfg &c, const double *scratch, int curve, int index) {
+__device__ __forceinline__ double eval_sample(const DevCfg &c, const double *coef, int curve, int index) {
     index = max(0, min(index, c.L - 1));
     int j, r;
     piece_of(c, index, j, r);
     const double s = (double)r * c.inv_Lm1;
-    const double *cf = scratch + (curve * c.npieces + j) * 4;
+    const double *cf = coef + (curve * c.npieces + j) * 4;
     return fma(fma(fma(cf[3], s, cf[2]), s, cf[1]), s, cf[0]);
 }
 
-// Called by all 32 lanes with warp-uniform arguments.  On return scratch[kCoefDoubles + m]
-// (m = 0..3) holds the folded coefficients of the first drawn curve's piece containing
-// sample `index_next` (exp 4/6: velocity, exp 5: the rect source) and [.. + 4 + m] those of
-// the second drawn curve (exp 6: angle).  The caller must __syncwarp() before the next call.
+// Called by all 32 lanes with warp-uniform arguments.  On return scratch[m] (m = 0..3) holds
+// the folded coefficients of the first drawn curve's piece containing sample `index_next`
+// (exp 4/6: velocity, exp 5: the rect source) and scratch[4 + m] those of the second drawn
+// curve (exp 6: angle).  The caller must __syncwarp() before the next call.
 static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long env_local, uint32_t episode,
                                                     int index_next, double *scratch) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int fp = c.fp, np = c.npieces, nc = c.ncurves;
     const long long genv = c.env_id_offset + env_local;
+    double *coef = scratch + 8;
 
     // --- knots: one per lane -----------------------------------------------------
     double u = 0.0;
@@ -73,7 +75,7 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
             const double uk = __shfl_sync(FULL, u, curve * fp + k);
             acc = fma(__ldg(row + k), uk, acc);
         }
-        if (valid) scratch[t] = acc;
+        if (valid) coef[t] = acc;
     }
     __syncwarp();
 
@@ -83,10 +85,10 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
     const int my_curve = (lane >= np) ? 1 : 0;
     if (lane < nc * np) {
         const int j = lane - my_curve * np;
-        const double *cf = scratch + (my_curve * np + j) * 4;
+        const double *cf = coef + (my_curve * np + j) * 4;
         const double c1 = cf[1], c2 = cf[2], c3 = cf[3];
         auto consider = [&](int index) {
-            const double v = eval_sample(c, scratch, my_curve, index);
+            const double v = eval_sample(c, coef, my_curve, index);
             mn = fmin(mn, v);
             mx = fmax(mx, v);
         };
@@ -133,7 +135,7 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
     piece_of(c, min(index_next, c.L - 1), jn, rn);
     if (lane < 4 * nc) {
         const int curve = lane >> 2, m = lane & 3;
-        const double cf = scratch[(curve * np + jn) * 4 + m];
+        const double cf = coef[(curve * np + jn) * 4 + m];
         const double lo = curve ? mnB : mnA, hi = curve ? mxB : mxA;
         double off = 0.0, inv = 1.0;
         if (lo < 0.0 || hi > 1.0) { off = lo; inv = 1.0 / (hi - lo); }
@@ -141,9 +143,9 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
         // itself; second curve of exp 6: curve * pi * 2 (wind.py:63)
         const double scale = curve ? 3.14159265358979323846 * 2.0
                                    : ((c.wind_kind == WIND_ANGLE_RECT) ? 1.0 : c.p.max_velocity);
-        scratch[kCoefDoubles + lane] = ((m == 0) ? (cf - off) : cf) * inv * scale;
+        scratch[lane] = ((m == 0) ? (cf - off) : cf) * inv * scale;
     } else if (lane < 8) {
-        scratch[kCoefDoubles + lane] = 0.0;
+        scratch[lane] = 0.0;
     }
     __syncwarp();
 }
