@@ -40,7 +40,7 @@ extern "C" {
 #define BOATENV_EEXPERIMENT (-2)   /* unknown experiment: the ValueError of wind.py:65-67   */
 #define BOATENV_EFIXEDPOINTS (-3)  /* fixed_points < 4: the ValueError of wind.py:73-75     */
 #define BOATENV_EUNSUPPORTED (-4)  /* valid for the reference, not for this build (e.g.
-                                      fixed_points > 16, t_max/dt > 2^24)                  */
+                                      fixed_points > 16, t_max/dt > 2^20)                  */
 #define BOATENV_ENODEVICE (-5)     /* no CUDA device / not an sm_100 device                 */
 #define BOATENV_ESTATE (-6)        /* step() before reset()                                 */
 #define BOATENV_EALIGN (-7)        /* a tensor pointer is not 16-byte aligned               */

@@ -29,6 +29,7 @@ struct boatenv_handle {
     size_t esize;
     bool was_reset;
     double *basis_dev;
+    int *piece_bounds_dev;
     int32_t *ovr_s_y;
     double *ovr_knots;
     double *counters_out_dev;  // 8 doubles
@@ -121,7 +122,7 @@ static int derive_config(const boatenv_params *p, DevCfg &c) {
     }
     c.npieces = c.fp - 1;
     const double Ld = p->t_max / p->dt;  // wind.py:14-15
-    if (!(Ld >= 2.0) || Ld > 16777216.0) return BOATENV_EUNSUPPORTED;
+    if (!(Ld >= 2.0) || Ld > 1048576.0) return BOATENV_EUNSUPPORTED;  // fp32 root location in wind_setup_warp
     if (Ld < 4.0) return BOATENV_EUNSUPPORTED;
     c.L = (int)Ld;
     c.Lm1 = c.L - 1;
@@ -275,6 +276,17 @@ int boatenv_create(const boatenv_params *params, int64_t n_envs, uint64_t seed, 
     if (e == cudaSuccess) e = cudaMemset(cfg.state, 0xFF, state_bytes);  // episode -1: reset() makes it 0
     if (e == cudaSuccess) e = cudaMemset(cfg.counters, 0, kCounterSlots * 32 * sizeof(double));
     cfg.basis = h->basis_dev;
+    {   // first / last sample of every spline piece: ceil(j*Lm1/np), floor((j+1)*Lm1/np)
+        std::vector<int> pb(2 * (size_t)cfg.npieces);
+        for (int j = 0; j < cfg.npieces; ++j) {
+            pb[2 * j] = (int)(((long long)j * cfg.Lm1 + cfg.npieces - 1) / cfg.npieces);
+            pb[2 * j + 1] = (int)(((long long)(j + 1) * cfg.Lm1) / cfg.npieces);
+        }
+        alloc((void **)&h->piece_bounds_dev, pb.size() * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemcpy(h->piece_bounds_dev, pb.data(), pb.size() * sizeof(int), cudaMemcpyHostToDevice);
+        cfg.piece_bounds = h->piece_bounds_dev;
+        cfg.per_piece = (float)((double)cfg.Lm1 / (double)cfg.npieces);
+    }
     h->cfg = cfg;
     if (e != cudaSuccess) {
         boatenv_destroy(h);
@@ -291,6 +303,7 @@ int boatenv_destroy(boatenv_t h) {
     cudaFree(h->cfg.counters);
     cudaFree(h->counters_out_dev);
     cudaFree(h->basis_dev);
+    cudaFree(h->piece_bounds_dev);
     cudaFree(h->ovr_s_y);
     cudaFree(h->ovr_knots);
     cudaFree(h->h_act);

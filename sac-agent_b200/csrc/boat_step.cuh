@@ -319,7 +319,7 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 #define BOAT_MINBLOCKS_F32 2  // 256-thread CTAs per SM the fp32 kernel is register-budgeted for
 #endif
 #ifndef BOAT_STAGES
-#define BOAT_STAGES 3         // state blocks in flight per warp (TMA pipeline depth)
+#define BOAT_STAGES 1         // state blocks in flight per warp beyond the one being computed (TMA pipeline depth)
 #endif
 template <typename T> struct StepTuning;
 template <> struct StepTuning<float> { static constexpr int kMinBlocks = BOAT_MINBLOCKS_F32; };
@@ -442,15 +442,19 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
         // state + per-env outputs of this launch (K = 1: right after the sub-step; K > 1: after the loop)
         auto store_results = [&]() {
             if (active) {
+#ifndef BOAT_DEBUG_SKIP_STATE
                 store_vecs<T, D_COUNT>(gb, lane, d);
                 __stcs(reinterpret_cast<uint2 *>(gb + c.off_idx) + lane, make_uint2((uint32_t)index, episode));
+#endif
                 if (KMULTI && wind_dirty) {  // wind coefficients change only on the slow path
                     if (kCurves) store_vecs<T, 4>(gb + c.off_wa, lane, wa);
                     if (WK == WIND_BOTH) store_vecs<T, 4>(gb + c.off_wb, lane, wb);
                 }
+#ifndef BOAT_DEBUG_SKIP_SMALL
                 __stcs(reinterpret_cast<T *>(a.reward_out) + i, rsum);
                 a.done_out[i] = (code != BOATENV_TERM_NONE) ? 1 : 0;
                 if (a.term_out) a.term_out[i] = (uint8_t)code;
+#endif
                 if (KMULTI) {
                     if (a.steps_out) a.steps_out[i] = nsteps;
                 }
@@ -507,21 +511,13 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             // ---- slow path: the warp serves its lanes one at a time ----
             if (__ballot_sync(FULL, need_setup && active)) {
                 const bool is_done = need_setup && active && code != BOATENV_TERM_NONE;
-                const unsigned dmask = __ballot_sync(FULL, is_done);
-                if (dmask) {  // statistics (info dict, boat_env.py:24-32,87-113): one atomic per counter per warp
+                if (is_done) {  // statistics (info dict, boat_env.py:24-32,87-113): sparse events -> per-env REDs
                     double *cnt = c.counters + (blk & (kCounterSlots - 1)) * 32;
-#pragma unroll
-                    for (int t = 1; t <= 5; ++t) {
-                        const unsigned m = __ballot_sync(FULL, is_done && code == t);
-                        if (lane == 0 && m) atomicAdd(cnt + (t - 1), (double)__popc(m));
-                    }
-                    const double ret = is_done ? (double)d[D_RET] : 0.0;
-                    const double s1 = warp_sum(ret), s2 = warp_sum(ret * ret);
-                    if (lane == 0) {
-                        atomicAdd(cnt + 5, (double)__popc(dmask));
-                        atomicAdd(cnt + 6, s1);
-                        atomicAdd(cnt + 7, s2);
-                    }
+                    const double ret = (double)d[D_RET];
+                    atomicAdd(cnt + (code - 1), 1.0);
+                    atomicAdd(cnt + 5, 1.0);
+                    atomicAdd(cnt + 6, ret);
+                    atomicAdd(cnt + 7, ret * ret);
                 }
                 if (is_done) {  // the terminal observation leaves before a reset overwrites the row
                     if (a.final_obs_out) {
@@ -606,11 +602,13 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
         if (rows == 32) {
             fence_proxy_async_smem();  // each lane: its st.shared rows -> visible to the async proxy
             __syncwarp();
+#ifndef BOAT_DEBUG_SKIP_OBS
             if (lane == 0) {
                 tma_store_1d(gobs, tile, kTileBytes);
                 tma_store_commit();
             }
             tile_in_flight = true;
+#endif
         } else {
             __syncwarp();
             for (int e = lane; e < rows * kObsDim; e += 32) gobs[e] = tile[e];

@@ -19,9 +19,11 @@
 
 namespace boatenv {
 
-// Per-warp scratch: [0..7] the folded result a[4], b[4]; [8..] the coefficient table [curve][piece][4].
-constexpr int kScratchDoubles = 8 + 2 * (kMaxKnots - 1) * 4;  // upper bound (static allocations)
-__host__ __device__ constexpr int scratch_doubles(int ncurves, int npieces) { return 8 + ncurves * npieces * 4; }
+// Per-warp scratch (doubles): [0..7] the folded result a[4], b[4]; [8..39] the knots
+// [curve][16]; [40..] the coefficient table [curve][piece][4].
+constexpr int kKnotOff = 8, kCoefOff = 8 + 2 * kMaxKnots;
+constexpr int kScratchDoubles = kCoefOff + 2 * (kMaxKnots - 1) * 4;  // upper bound (static allocations)
+__host__ __device__ constexpr int scratch_doubles(int ncurves, int npieces) { return kCoefOff + ncurves * npieces * 4; }
 
 // Piece index and local coordinate numerator of wind sample `index` (0 <= index < L):
 // x_index / h = index * (fp-1) / (L-1) exactly (x_index = index * L/(L-1), h = L/(fp-1)),
@@ -35,6 +37,7 @@ __device__ __forceinline__ void piece_of(const DevCfg &c, int index, int &j, int
     r = (int)(num - q * (uint32_t)c.Lm1);
 }
 
+// Value of sample `index` of curve `curve` before renormalisation (fp64 Horner on the piece table).
 __device__ __forceinline__ double eval_sample(const DevCfg &c, const double *coef, int curve, int index) {
     index = max(0, min(index, c.L - 1));
     int j, r;
@@ -48,102 +51,106 @@ __device__ __forceinline__ double eval_sample(const DevCfg &c, const double *coe
 // the folded coefficients of the first drawn curve's piece containing sample `index_next`
 // (exp 4/6: velocity, exp 5: the rect source) and scratch[4 + m] those of the second drawn
 // curve (exp 6: angle).  The caller must __syncwarp() before the next call.
+// Lane map: half-warp h = lane >> 4 works on curve h, sub-lane k = lane & 15 on knot / piece k.
 static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long env_local, uint32_t episode,
                                                     int index_next, double *scratch) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int fp = c.fp, np = c.npieces, nc = c.ncurves;
-    const long long genv = c.env_id_offset + env_local;
-    double *coef = scratch + 8;
+    const int cv = lane >> 4, sub = lane & 15;
+    double *kn = scratch + kKnotOff, *coef = scratch + kCoefOff;
 
-    // --- knots: one per lane -----------------------------------------------------
-    double u = 0.0;
-    if (lane < nc * fp)
-        u = c.ovr_knots ? c.ovr_knots[env_local * 2 * fp + lane] : episode_knot(c.seed, genv, episode, lane);
+    // --- knots (wind.py:78): lane (cv, sub) draws knot sub of curve cv -----------------
+    if (cv < nc && sub < fp)
+        kn[cv * kMaxKnots + sub] = c.ovr_knots ? c.ovr_knots[env_local * 2 * fp + cv * fp + sub]
+                                               : episode_knot(c.seed, c.env_id_offset + env_local, episode, cv * fp + sub);
+    __syncwarp();
 
-    // --- piece coefficients in the local coordinate s: c_m = sum_k basis[j][m][k] u_k --
+    // --- piece coefficients in the local coordinate s: c_m = sum_k basis[j][m][k] u_k ---
     const int total = nc * np * 4;
     for (int base = 0; base < total; base += 32) {
         const int t = base + lane;
-        const bool valid = t < total;
-        const int tt = valid ? t : 0;
-        const int curve = (tt >= np * 4) ? 1 : 0;
-        const int rem = tt - curve * np * 4;
-        const double *row = c.basis + (size_t)rem * fp;  // rem = piece * 4 + m
-        double acc = 0.0;
-        for (int k = 0; k < fp; ++k) {
-            const double uk = __shfl_sync(FULL, u, curve * fp + k);
-            acc = fma(__ldg(row + k), uk, acc);
+        if (t < total) {
+            const int curve = (t >= np * 4) ? 1 : 0;
+            const int rem = t - curve * np * 4;              // piece * 4 + m
+            const double *brow = c.basis + (size_t)rem * fp;
+            const double *u = kn + curve * kMaxKnots;
+            double acc0 = 0.0, acc1 = 0.0;
+            int k = 0;
+            for (; k + 1 < fp; k += 2) {
+                acc0 = fma(__ldg(brow + k), u[k], acc0);
+                acc1 = fma(__ldg(brow + k + 1), u[k + 1], acc1);
+            }
+            if (k < fp) acc0 = fma(__ldg(brow + k), u[k], acc0);
+            coef[t] = acc0 + acc1;
         }
-        if (valid) coef[t] = acc;
     }
     __syncwarp();
 
-    // --- extremal samples of every piece -------------------------------------------
+    // --- extremal samples of every piece (np.min / np.max of wind.py:87-89) -----------------
+    // The discrete extremes of a piece sit at its end samples or next to a root of the derivative;
+    // the roots are LOCATED in fp32 (a 4-sample window absorbs the location error), the candidate
+    // samples are EVALUATED in fp64.
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     double mn = inf, mx = -inf;
-    const int my_curve = (lane >= np) ? 1 : 0;
-    if (lane < nc * np) {
-        const int j = lane - my_curve * np;
-        const double *cf = coef + (my_curve * np + j) * 4;
-        const double c1 = cf[1], c2 = cf[2], c3 = cf[3];
+    if (cv < nc && sub < np) {
+        const double *cf = coef + (cv * np + sub) * 4;
         auto consider = [&](int index) {
-            const double v = eval_sample(c, coef, my_curve, index);
+            const double v = eval_sample(c, coef, cv, index);
             mn = fmin(mn, v);
             mx = fmax(mx, v);
         };
-        // first / last sample that falls into this piece
-        consider((j * c.Lm1 + np - 1) / np);
-        consider(((j + 1) * c.Lm1) / np);
-        // roots of the derivative c1 + 2 c2 s + 3 c3 s^2
-        const double A = 3.0 * c3, B = 2.0 * c2, C0 = c1;
-        const double nan = __longlong_as_double(0x7ff8000000000000LL);
-        double s1 = nan, s2 = nan;
-        if (fabs(A) > 1e-14 * (fabs(B) + fabs(C0))) {
-            const double disc = B * B - 4.0 * A * C0;
-            if (disc >= 0.0) {
-                const double q = -0.5 * (B + copysign(sqrt(disc), B));
-                s1 = q / A;
-                if (q != 0.0) s2 = C0 / q;
+        consider(__ldg(c.piece_bounds + 2 * sub));      // first sample that falls into this piece
+        consider(__ldg(c.piece_bounds + 2 * sub + 1));  // last one
+        const float A = 3.0f * (float)cf[3], B = 2.0f * (float)cf[2], C0 = (float)cf[1];
+        const float nanf_ = __int_as_float(0x7fc00000);
+        float s1 = nanf_, s2 = nanf_;
+        if (fabsf(A) > 1e-6f * (fabsf(B) + fabsf(C0))) {
+            const float disc = fmaf(B, B, -4.0f * A * C0);
+            if (disc >= 0.0f) {
+                const float q = -0.5f * (B + copysignf(sqrtf(disc), B));
+                s1 = __fdividef(q, A);
+                if (q != 0.0f) s2 = __fdividef(C0, q);
             }
-        } else if (B != 0.0) {
-            s1 = -C0 / B;
+        } else if (B != 0.0f) {
+            s1 = __fdividef(-C0, B);
         }
-        const double per_piece = (double)c.Lm1 / (double)np;  // samples per piece
-        const double margin = 2.0 / per_piece;
-        if (s1 > -margin && s1 < 1.0 + margin) {
-            const int f = (int)floor(((double)j + s1) * per_piece);
-            consider(f);
-            consider(f + 1);
-        }
-        if (s2 > -margin && s2 < 1.0 + margin) {
-            const int f = (int)floor(((double)j + s2) * per_piece);
-            consider(f);
-            consider(f + 1);
+        const float per_piece = c.per_piece, margin = 3.0f / per_piece;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const float sr = which ? s2 : s1;
+            if (sr > -margin && sr < 1.0f + margin) {
+                const int f = (int)floorf(((float)sub + sr) * per_piece);
+                consider(f - 1);
+                consider(f);
+                consider(f + 1);
+                consider(f + 2);
+            }
         }
     }
-    const bool inA = lane < np, inB = (lane >= np) && (lane < 2 * np) && nc == 2;
-    const double mnA = warp_min(inA ? mn : inf), mxA = warp_max(inA ? mx : -inf);
-    double mnB = 0.0, mxB = 1.0;
-    if (nc == 2) {
-        mnB = warp_min(inB ? mn : inf);
-        mxB = warp_max(inB ? mx : -inf);
+    // segmented reduction: each half-warp reduces its own curve
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(FULL, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
     }
+    // lanes 0..15 hold curve A's extremes, 16..31 curve B's; lanes 0..7 do the fold
+    const double mnB = __shfl_sync(FULL, mn, 16), mxB = __shfl_sync(FULL, mx, 16);
 
     // --- fold renormalisation (wind.py:87-89) and the experiment's scale: lanes 0..7 --
     int jn, rn;
     piece_of(c, min(index_next, c.L - 1), jn, rn);
     if (lane < 4 * nc) {
         const int curve = lane >> 2, m = lane & 3;
-        const double cf = coef[(curve * np + jn) * 4 + m];
-        const double lo = curve ? mnB : mnA, hi = curve ? mxB : mxA;
+        const double cfm = coef[(curve * np + jn) * 4 + m];
+        const double lo = curve ? mnB : mn, hi = curve ? mxB : mx;
         double off = 0.0, inv = 1.0;
         if (lo < 0.0 || hi > 1.0) { off = lo; inv = 1.0 / (hi - lo); }
         // exp 4 / 6: curve * max_velocity (wind.py:49,62); exp 5: the rect threshold acts on the curve
         // itself; second curve of exp 6: curve * pi * 2 (wind.py:63)
         const double scale = curve ? 3.14159265358979323846 * 2.0
                                    : ((c.wind_kind == WIND_ANGLE_RECT) ? 1.0 : c.p.max_velocity);
-        scratch[lane] = ((m == 0) ? (cf - off) : cf) * inv * scale;
+        scratch[lane] = ((m == 0) ? (cfm - off) : cfm) * inv * scale;
     } else if (lane < 8) {
         scratch[lane] = 0.0;
     }
