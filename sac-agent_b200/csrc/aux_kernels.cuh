@@ -136,19 +136,34 @@ static __global__ void boat_reduce_counters_kernel(const double *counters, doubl
     }
 }
 
-// uniform(-1,1) * scale actions from Philox(seed, global env, step_counter): the policy
-// "A1" of SURVEY.md 8(d).  24-bit values, exactly representable in fp32.
+// uniform(-1,1) * scale actions: the policy "A1" of SURVEY.md 8(d).  One Philox4x32-10 call
+// yields the actions of FOUR consecutive global envs: env g at step t gets word (g & 3) of
+// Philox(counter = (g >> 2, t), key = seed), as a 23-bit value exactly representable in fp32.
+// One thread per global quad, 128-bit stores when the shard starts on a quad boundary.
 template <typename T>
-__global__ void boat_fill_actions_kernel(const __grid_constant__ DevCfg c, unsigned long long step_counter,
-                                         double scale, T *out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n_envs) return;
-    const long long g = c.env_id_offset + i;
-    const Philox4 r = philox4x32_10((uint32_t)g, (uint32_t)((unsigned long long)g >> 32), (uint32_t)step_counter,
+__global__ void __launch_bounds__(256) boat_fill_actions_kernel(const __grid_constant__ DevCfg c,
+                                                                unsigned long long step_counter, double scale, T *out) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // quad index within the shard
+    const long long quad = (c.env_id_offset >> 2) + q;                     // global quad
+    const long long first = quad * 4 - c.env_id_offset;                    // local index of the quad's first env
+    if (first >= c.n_envs) return;
+    const Philox4 r = philox4x32_10((uint32_t)quad, (uint32_t)((unsigned long long)quad >> 32), (uint32_t)step_counter,
                                     kStreamAction | (uint32_t)((step_counter >> 32) & 0x0fffffffu), (uint32_t)c.seed,
                                     (uint32_t)(c.seed >> 32));
-    const float u = (float)(r.x >> 8) * (1.0f / 8388608.0f) - 1.0f;
-    out[i] = (T)((float)scale * u);
+    const float sc = (float)scale;
+    T v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (T)(sc * ((float)(philox_word(r, k) >> 8) * (1.0f / 8388608.0f) - 1.0f));
+    if (first >= 0 && first + 4 <= c.n_envs && ((reinterpret_cast<uintptr_t>(out + first) & 15u) == 0)) {
+        using V = typename VecOf<T>::type;
+        constexpr int W = VecOf<T>::W;
+#pragma unroll
+        for (int k = 0; k < 4 / W; ++k) __stcs(reinterpret_cast<V *>(out + first) + k, pack(&v[k * W]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (first + k >= 0 && first + k < c.n_envs) out[first + k] = v[k];
+    }
 }
 
 }  // namespace boatenv

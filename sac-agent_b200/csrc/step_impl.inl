@@ -80,8 +80,9 @@ cudaError_t FN(launch_set_field_)(const DevCfg &c, int field, const void *in, cu
 
 cudaError_t FN(launch_fill_actions_)(const DevCfg &c, unsigned long long step_counter, double scale, void *out,
                                      cudaStream_t st) {
-    boat_fill_actions_kernel<REAL><<<grid_for(c.n_envs, 256), 256, 0, st>>>(c, step_counter, scale,
-                                                                           reinterpret_cast<REAL *>(out));
+    const long long quads = (c.n_envs + (c.env_id_offset & 3) + 3) / 4;  // global quads touched by this shard
+    boat_fill_actions_kernel<REAL><<<grid_for(quads, 256), 256, 0, st>>>(c, step_counter, scale,
+                                                                        reinterpret_cast<REAL *>(out));
     count_launch();
     return cudaGetLastError();
 }

@@ -271,6 +271,13 @@ def test_shard_invariance(S):
         oh, rh, dh, _ = hi.step(aw[512:])
         assert torch.equal(ow[:512], ol) and torch.equal(ow[512:], oh)
         assert torch.equal(rw[:512], rl) and torch.equal(dw[512:], dh)
+    # the action stream is keyed by global env id too, also across an odd (non quad-aligned) split
+    odd_lo = make_env(S, cfg, 513, "fp32", seed=11, env_id_offset=0)
+    odd_hi = make_env(S, cfg, 511, "fp32", seed=11, env_id_offset=513)
+    aw = whole.uniform_actions(5, 0.7)
+    assert torch.equal(aw[:513], odd_lo.uniform_actions(5, 0.7)) and torch.equal(aw[513:], odd_hi.uniform_actions(5, 0.7))
+    assert float(aw.abs().max()) <= 0.7 and float(aw.std()) == pytest.approx(0.7 / 3 ** 0.5, rel=0.1)
+    odd_lo.close(); odd_hi.close()
     cw, cl, ch = whole.counters(), lo.counters(), hi.counters()
     assert cw["episodes"] > 0
     for k in ("reached_goal", "out_of_bounds", "out_of_fuel", "timeout", "rudder_broken", "episodes"):
