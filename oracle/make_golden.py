@@ -59,6 +59,24 @@ def cardinal_basis(L: int, n_knots: int) -> np.ndarray:
     return W
 
 
+def rect_knots_from_switches(wa, W):
+    """Fixture 5 records only the rectified direction (pi/2 <-> 3pi/2, wind.py:92-99), which pins
+    the sign of (curve - 0.25) at every sample but not the knots.  Any knot vector with that sign
+    pattern (and a curve inside [0,1], so that wind.py:87 does not renormalise) reproduces the
+    recorded wind table exactly; pick the one with the largest margin (a small LP)."""
+    from scipy.optimize import linprog
+    L, k = W.shape
+    s = np.where(wa > np.pi, 1.0, -1.0)
+    A = np.vstack([np.hstack([-(s[:, None] * W), np.ones((L, 1))]),
+                   np.hstack([W, np.zeros((L, 1))]), np.hstack([-W, np.zeros((L, 1))])])
+    b = np.concatenate([-0.25 * s, np.full(L, 0.98), np.full(L, -0.02)])
+    res = linprog(c=[0] * k + [-1], A_ub=A, b_ub=b, bounds=[(0.01, 0.99)] * k + [(0, 0.2)], method="highs")
+    assert res.status == 0 and res.x[k] > 1e-6, res.message
+    u = res.x[:k]
+    assert np.array_equal(W @ u > 0.25, wa > np.pi)
+    return u, float(res.x[k])
+
+
 # --------------------------------------------------------------------------
 # 1. the reference's recorded fixtures
 # --------------------------------------------------------------------------
@@ -73,7 +91,7 @@ def condense_fixture(n: int):
     wv, wa = wind.wind_velocity.values.astype(float), wind.wind_angle.values.astype(float)
     W = cardinal_basis(L, int(cfg.wind.fixed_points))
     rec = dict(kind_v="const", kind_a="const", const_v=float(wv[0]), const_a=float(wa[0]))
-    knots_v = knots_a = np.zeros(0)
+    knots_v = knots_a = knots_r = np.zeros(0)
     switches = np.zeros(0, dtype=np.int64)
     if n in (4, 6):  # velocity = curve * max_velocity   (wind.py:49,62)
         knots_v, *_ = np.linalg.lstsq(W, wv / float(cfg.wind.max_velocity), rcond=None)
@@ -87,6 +105,7 @@ def condense_fixture(n: int):
         switches = np.flatnonzero(np.diff(wa) != 0) + 1
         rec["kind_a"] = "rect"
         rec["rect_levels"] = sorted(set(np.round(wa, 12).tolist()))
+        knots_r, rec["rect_margin"] = rect_knots_from_switches(wa, W)
     rows = np.unique(np.concatenate([np.arange(0, 8), np.arange(0, len(data), 37),
                                      np.arange(len(data) - 8, len(data))]))
     cols = ["boat_position_x", "boat_position_y", "boat_velocity_x", "boat_velocity_y",
@@ -98,7 +117,7 @@ def condense_fixture(n: int):
         n_rows=len(data), termination=str(info.termination[0]),
         episode_reward=float(info.episode_reward[0]),
         s_y_start=int(round(float(data.boat_position_y[0]))),
-        knots_v=knots_v, knots_a=knots_a, angle_switches=switches, angle0=float(wa[0]),
+        knots_v=knots_v, knots_a=knots_a, knots_r=knots_r, angle_switches=switches, angle0=float(wa[0]),
         wind_idx=wsub, wind_v=wv[wsub], wind_a=wa[wsub],
         row_idx=rows, rows=data[cols].values[rows].astype(float), columns=json.dumps(cols))
     print(f"fixture {n}: rows={len(data)} L={L} {rec}")

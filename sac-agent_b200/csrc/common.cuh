@@ -17,7 +17,10 @@
 namespace boatenv {
 
 constexpr int kObsDim = BOATENV_OBS_DIM;
-constexpr int kTile = 256;      // envs per CTA tile == threads per CTA
+#ifndef BOAT_CTA_THREADS
+#define BOAT_CTA_THREADS 256
+#endif
+constexpr int kTile = BOAT_CTA_THREADS;  // threads per CTA (8 self-contained warps)
 constexpr int kWarpsPerCta = kTile / 32;
 constexpr int kMaxKnots = 16;   // fixed_points supported by this build (reference default 8)
 constexpr int kCounterSlots = 32;  // replicated counter rows (spread atomics over L2 slices)

@@ -113,7 +113,7 @@ def test_golden_rollouts_fp32(S, name):
 # ---------------------------------------------------------------------------------------
 # 2. the reference's recorded fixtures (ressources/settings_visualized): known answers
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 6])  # fixture 5 pins only switch positions, not knots
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6])
 def test_recorded_fixture_replay(S, n):
     g = load_golden(f"fixture_exp{n}")
     fp = int(g["config"]["wind"]["fixed_points"])
@@ -122,6 +122,8 @@ def test_recorded_fixture_replay(S, n):
         knots[0, 0] = g["knots_v"]
     if g["meta"]["kind_a"] == "curve":
         knots[0, 1] = g["knots_a"]
+    if g["meta"]["kind_a"] == "rect":  # exp 5: the first drawn curve is the rect source (wind.py:57)
+        knots[0, 0] = g["knots_r"]
     env = make_env(S, g["config"], 1, "fp64", np.array([int(g["s_y_start"])]), knots, auto_reset=False)
     env.reset()
     wv, wa = env.wind_table(0)

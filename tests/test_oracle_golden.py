@@ -23,12 +23,18 @@ def fixture_wind_tables(g, params):
     if meta["kind_a"] == "curve":
         wa = O.random_curve(g["knots_a"], L) * np.pi * 2
     if meta["kind_a"] == "rect":
+        # knots recovered from the recorded switch pattern (make_golden.rect_knots_from_switches):
+        # the oracle's own wind.py:53-58 path must reproduce the recorded table from them
+        exp5 = O.OracleEnv(params)
+        exp5.reset(0, g["knots_r"], np.zeros(len(g["knots_r"])))
+        wa_from_knots = exp5.wind()[1]
         lo, hi = np.pi / 2, np.pi + np.pi / 2
         cur = float(g["angle0"])
         edges = [0] + list(g["angle_switches"]) + [L]
         for a, b in zip(edges[:-1], edges[1:]):
             wa[a:b] = cur
             cur = hi if abs(cur - lo) < 1e-9 else lo
+        assert np.array_equal(wa_from_knots, wa)
     return wv, wa
 
 
