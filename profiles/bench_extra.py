@@ -60,12 +60,20 @@ def boat_case(name, experiment, precision, n, scale, bytes_per_step, warm, iters
     for _ in range(warm):
         step()
 
-    def only_step():
+    # fresh actions every step (a repeated action tensor would drive every rudder to its limit within
+    # ~20 steps); only the step launch sits between the event pairs, like in bench.py
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in pairs:
+        env.uniform_actions(t[0], scale, out=acts)
+        a.record()
         if k == 1:
             env.step(acts)
         else:
             env.step_k(acts, k)
-    ms = timed(only_step, iters, warmup=2)
+        b.record()
+        t[0] += 1
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in pairs) / iters
     emit(name, ms, n * k, "env-steps", bytes_per_step, n_envs=n, precision=precision, experiment=experiment, k=k,
          episodes=env.counters()["episodes"])
     env.close()
@@ -106,7 +114,14 @@ def main():
     for t in range(300):
         env.uniform_actions(t, 1.0, out=acts)
         env.step(acts)
-    ms = timed(lambda: big.step_store(env, acts), 50, warmup=2)
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+    for t, (e0, e1) in enumerate(pairs, start=300):
+        env.uniform_actions(t, 1.0, out=acts)
+        e0.record()
+        big.step_store(env, acts)
+        e1.record()
+    torch.cuda.synchronize()
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in pairs) / len(pairs)
     emit("exp6_fp32_16M_fused_step_store", ms, 16 * M, "env-steps", 165 + 44 + 97,
          note="step (165 B) + previous obs read (44 B) + transition written (97 B)")
     env.close(); big.close(); buf.close()

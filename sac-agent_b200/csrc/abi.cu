@@ -28,6 +28,7 @@ struct boatenv_handle {
     int precision, device;
     size_t esize;
     bool was_reset;
+    unsigned launch_parity;    // consecutive step launches sweep the state in opposite directions
     double *basis_dev;
     int *piece_bounds_dev;
     int32_t *ovr_s_y;
@@ -332,6 +333,9 @@ int boatenv_reset(boatenv_t h, const uint8_t *mask, void *obs_out, void *stream)
 
 static int step_common(boatenv_t h, StepArgs &a, cudaStream_t st) {
     if (!h->was_reset) return BOATENV_ESTATE;
+#ifndef BOAT_NO_REVERSE
+    a.reverse = (int)(h->launch_parity++ & 1u);
+#endif
     if (!a.actions || !a.obs_out || !a.reward_out || !a.done_out || a.ksteps < 1) return BOATENV_EINVAL;
     if (!aligned16(a.obs_out)) return BOATENV_EALIGN;
     CUDA_TRY(cudaSetDevice(h->device));
@@ -408,6 +412,7 @@ int boatenv_step_host(boatenv_t h, const void *actions_host, void *obs_host, voi
     int nchunks = n >= 8LL * 65536 ? 8 : (n >= 4LL * 65536 ? 4 : 1);
     long long per = ((n + nchunks - 1) / nchunks + kTile - 1) / kTile * kTile;
     const size_t es = h->esize;
+    const int rev = (int)(h->launch_parity++ & 1u);
     for (int cidx = 0; cidx < nchunks; ++cidx) {
         const long long b = (long long)cidx * per, e = std::min(n, b + per);
         if (b >= e) break;
@@ -426,6 +431,7 @@ int boatenv_step_host(boatenv_t h, const void *actions_host, void *obs_host, voi
         a.reward_out = h->h_rew;
         a.done_out = h->h_done;
         a.flags = flags;
+        a.reverse = rev;
         CUDA_TRY(h->precision == 32 ? launch_step_f32(h->cfg, a, h->compute) : launch_step_f64(h->cfg, a, h->compute));
         CUDA_TRY(cudaEventRecord(h->ev_k[cidx], h->compute));
         CUDA_TRY(cudaStreamWaitEvent(h->copy_out, h->ev_k[cidx], 0));
@@ -533,4 +539,5 @@ DevCfg *handle_cfg(boatenv_t h) { return &h->cfg; }
 int handle_precision(boatenv_t h) { return h->precision; }
 int handle_device(boatenv_t h) { return h->device; }
 bool handle_was_reset(boatenv_t h) { return h->was_reset; }
+int handle_next_parity(boatenv_t h) { return (int)(h->launch_parity++ & 1u); }
 }  // namespace boatenv

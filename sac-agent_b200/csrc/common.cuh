@@ -102,6 +102,7 @@ struct StepArgs {
     int32_t *steps_out;
     const void *obs_in;        // previous observations (fused replay store only)
     uint32_t flags;
+    int reverse;               // sweep direction of this launch (alternates, see boat_step.cuh)
     ReplayView rp;
 };
 
@@ -210,14 +211,22 @@ __device__ __forceinline__ void load_vecs(const char *sec, int lane, T (&out)[NS
     for (int v = 0; v < NS / W; ++v) unpack(p[v * 32], &out[v * W]);
 }
 
-// Streaming (evict-first) 128-bit stores of NS scalars: every byte of state is written once per step.
+// State stores: default (evict-normal) L2 policy, unlike the streamed outputs: the state is the only
+// data the NEXT launch reads again, and launches alternate their sweep direction (boat_step.cuh).
+#ifdef BOAT_STATE_STCS
+template <typename V> __device__ __forceinline__ void st_state(V *p, const V &v) { __stcs(p, v); }
+#else
+template <typename V> __device__ __forceinline__ void st_state(V *p, const V &v) { *p = v; }
+#endif
+
+// 128-bit stores of NS scalars of lane `lane` into a section.
 template <typename T, int NS>
 __device__ __forceinline__ void store_vecs(char *sec, int lane, const T (&in)[NS]) {
     using V = typename VecOf<T>::type;
     constexpr int W = VecOf<T>::W;
     V *p = reinterpret_cast<V *>(sec) + lane;
 #pragma unroll
-    for (int v = 0; v < NS / W; ++v) __stcs(p + v * 32, pack(&in[v * W]));
+    for (int v = 0; v < NS / W; ++v) st_state(p + v * 32, pack(&in[v * W]));
 }
 
 // Plain per-array SoA helpers (toy envs: 4 scalars per env in [vector][env] order).

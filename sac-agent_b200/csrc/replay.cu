@@ -23,6 +23,7 @@ DevCfg *handle_cfg(boatenv_t h);
 int handle_precision(boatenv_t h);
 int handle_device(boatenv_t h);
 bool handle_was_reset(boatenv_t h);
+int handle_next_parity(boatenv_t h);
 }  // namespace boatenv
 
 struct boatreplay_handle {
@@ -266,6 +267,7 @@ int boatenv_step_store(boatenv_t h, boatreplay_t r, const void *actions, void *o
     a.rp.mem_size = r->mem_size;
     a.rp.base_slot = r->mem_cntr % r->mem_size;
     a.rp.done_flag_mode = done_flag_mode;
+    a.reverse = boatenv::handle_next_parity(h);
     CUDA_TRY(r->precision == 32 ? launch_step_f32(c, a, (cudaStream_t)stream)
                                 : launch_step_f64(c, a, (cudaStream_t)stream));
     r->mem_cntr += c.n_envs;
