@@ -327,16 +327,77 @@ template <> struct StepTuning<float> { static constexpr int kMinBlocks = BOAT_MI
 template <> struct StepTuning<double> { static constexpr int kMinBlocks = 1; };
 constexpr int kStages = BOAT_STAGES;
 
-// Shared memory of one warp (dynamic smem, carved per warp): the TMA stages, the observation
-// staging tile, the slow-path scratch and the stage barriers.
+#ifndef BOAT_SETUP_WARPS
+#define BOAT_SETUP_WARPS 4    // dedicated wind-setup warps per CTA in the K = 1 kernels of experiments 4-6
+#endif
+// K = 1 kernels of the random-wind experiments run warp-specialised: 8 step warps stream the state
+// and push their (rare) wind-setup requests into a shared-memory queue, kSetup extra warps serve it.
+template <int WK, bool KMULTI>
+__host__ __device__ constexpr int setup_warps() {
+    return (!KMULTI && (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH)) ? BOAT_SETUP_WARPS : 0;
+}
+
+// Bounded multi-producer / multi-consumer ring in shared memory (ticket + per-slot sequence number).
+// Producers: lanes of the step warps (one request per env that needs new wind coefficients);
+// consumers: the setup warps.  A full ring blocks the producer, consumers always make progress.
+constexpr int kQueueSlots = 64;
+struct SetupRequest { int env; uint32_t episode; int index_next; int pad; };
+struct SetupQueue {
+    unsigned tail, head, producers_done, pad;
+    unsigned seq[kQueueSlots];
+    SetupRequest slot[kQueueSlots];
+};
+
+__device__ __forceinline__ void queue_push(SetupQueue *q, const SetupRequest &r) {
+    const unsigned ticket = atomicAdd(&q->tail, 1u);
+    const unsigned s = ticket % kQueueSlots;
+    volatile unsigned *seq = q->seq + s;
+    while (*seq != ticket) __nanosleep(64);      // slot still holds an unconsumed older request
+    q->slot[s] = r;
+    __threadfence_block();
+    *seq = ticket + 1u;                           // publish
+}
+
+// Called by lane 0 of a setup warp.  Returns false when every producer has finished and the ring is drained.
+__device__ __forceinline__ bool queue_pop(SetupQueue *q, int n_producers, SetupRequest &r) {
+    const unsigned ticket = atomicAdd(&q->head, 1u);
+    const unsigned s = ticket % kQueueSlots;
+    volatile unsigned *seq = q->seq + s;
+    volatile unsigned *done = &q->producers_done, *tail = &q->tail;
+    while (*seq != ticket + 1u) {
+        if (*done == (unsigned)n_producers && (int)(ticket - *tail) >= 0) return false;
+        __nanosleep(128);
+    }
+    __threadfence_block();
+    r = q->slot[s];
+    __threadfence_block();
+    *seq = ticket + kQueueSlots;                  // free the slot for its next ticket
+    return true;
+}
+
+// Dynamic shared memory of a CTA: per step warp the TMA stages, the observation staging tile,
+// (inline slow path only) the scratch, the stage barriers; then the request queue and the
+// scratch of the setup warps.
 template <typename T>
 struct WarpSmem {
     int tile_off, scratch_off, bar_off, bytes;
-    __host__ __device__ WarpSmem(int block_bytes, int ncurves, int npieces) {
+    __host__ __device__ WarpSmem(int block_bytes, int scratch_dbl) {
         tile_off = kStages * block_bytes;
         scratch_off = tile_off + 32 * kObsDim * (int)sizeof(T);
-        bar_off = scratch_off + scratch_doubles(ncurves, npieces) * 8;
+        bar_off = scratch_off + scratch_dbl * 8;
         bytes = (bar_off + kStages * 8 + 127) / 128 * 128;
+    }
+};
+template <typename T>
+struct CtaSmem {
+    WarpSmem<T> warp;
+    int queue_off, setup_scratch_off, setup_scratch_bytes, bytes;
+    __host__ __device__ CtaSmem(int block_bytes, int ncurves, int npieces, int n_setup)
+        : warp(block_bytes, n_setup > 0 ? 0 : scratch_doubles(ncurves, npieces)) {
+        queue_off = kWarpsPerCta * warp.bytes;
+        setup_scratch_off = queue_off + (n_setup > 0 ? (int)sizeof(SetupQueue) : 0);
+        setup_scratch_bytes = (scratch_doubles(ncurves, npieces) * 8 + 127) / 128 * 128;
+        bytes = setup_scratch_off + n_setup * setup_scratch_bytes;
     }
 };
 
@@ -351,16 +412,51 @@ struct WarpSmem {
 // written back right after the sub-step and the (rare) slow path patches the affected envs
 // in global memory, so that almost nothing is live in registers across the slow path.
 template <typename T, int WK, bool KMULTI>
-__global__ void __launch_bounds__(kTile, StepTuning<T>::kMinBlocks)
+__global__ void __launch_bounds__(kTile + 32 * setup_warps<WK, KMULTI>(), StepTuning<T>::kMinBlocks)
 boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool kCurves = (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH);
+    constexpr int kSetup = setup_warps<WK, KMULTI>();
     constexpr int kTileBytes = 32 * kObsDim * (int)sizeof(T);
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bb = c.block_bytes;
 
-    const WarpSmem<T> lay(bb, c.ncurves, c.npieces);
+    const CtaSmem<T> cta(bb, c.ncurves, c.npieces, kSetup);
+    const WarpSmem<T> &lay = cta.warp;
+    SetupQueue *queue = reinterpret_cast<SetupQueue *>(smem_raw + cta.queue_off);
+    if (kSetup > 0) {
+        for (int t = threadIdx.x; t < kQueueSlots; t += blockDim.x) queue->seq[t] = (unsigned)t;
+        if (threadIdx.x == 0) { queue->tail = 0u; queue->head = 0u; queue->producers_done = 0u; }
+        __syncthreads();  // the only CTA-wide barrier: once, before any work
+        if (warp >= kWarpsPerCta) {
+            // ===== setup warps: serve wind-setup requests until the step warps are done and the ring is empty =====
+            double *scr = reinterpret_cast<double *>(smem_raw + cta.setup_scratch_off +
+                                                     (warp - kWarpsPerCta) * cta.setup_scratch_bytes);
+            for (;;) {
+                SetupRequest r;
+                r.env = -1; r.episode = 0u; r.index_next = 0; r.pad = 0;
+                if (lane == 0 && !queue_pop(queue, kWarpsPerCta, r)) r.env = -1;
+                const int env = __shfl_sync(FULL, r.env, 0);
+                if (env < 0) break;
+                const uint32_t epi = __shfl_sync(FULL, r.episode, 0);
+                const int idx_next = __shfl_sync(FULL, r.index_next, 0);
+#ifdef BOAT_DEBUG_SKIP_SETUP  // experiment only: requests are popped and dropped
+                continue;
+#endif
+                wind_setup_warp(c, (long long)env, epi, idx_next, scr);
+                if (lane < 2 && (lane == 0 || WK == WIND_BOTH)) {  // lane 0: first curve, lane 1: second curve
+                    T w4[4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) w4[m] = (T)scr[lane * 4 + m];
+                    char *gb = c.state + (size_t)(env >> 5) * (size_t)bb;
+                    store_vecs<T, 4>(gb + (lane ? c.off_wb : c.off_wa), env & 31, w4);
+                }
+                __syncwarp();
+            }
+            return;
+        }
+    }
     unsigned char *wbase = smem_raw + (size_t)warp * lay.bytes;
     unsigned char *stage_base = wbase;                                  // kStages * bb   (16-byte aligned)
     T *tile = reinterpret_cast<T *>(wbase + lay.tile_off);              // [32][11]
@@ -377,7 +473,10 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
     const int blk_first = (int)(a.env_begin >> 5), blk_last = blk_end - 1;
     const bool rev = a.reverse != 0;
     int seq = blk_first + (int)blockIdx.x * kWarpsPerCta + warp;
-    if (seq >= blk_end) return;
+    if (seq >= blk_end) {
+        if (kSetup > 0 && lane == 0) atomicAdd(&queue->producers_done, 1u);
+        return;
+    }
     auto block_of = [&](int q) { return rev ? (blk_last - (q - blk_first)) : q; };
 
     const uint64_t pol = policy_evict_first();
@@ -542,7 +641,28 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                         next_stored = true;
                     }
                 }
-                unsigned todo = __ballot_sync(FULL, need_setup && active && (!is_done || auto_reset));
+                if (kSetup > 0) {
+                    // warp-specialised K = 1 path: the env's own lane does the cheap part (Boat.__init__ state,
+                    // reset observation) and hands the wind coefficients to the setup warps
+                    if (need_setup && active && (!is_done || auto_reset)) {
+                        SetupRequest rq;
+                        rq.env = i;
+                        rq.episode = episode + (is_done ? 1u : 0u);
+                        rq.index_next = is_done ? 0 : index;
+                        rq.pad = 0;
+#ifndef BOAT_DEBUG_SKIP_PUSH
+                        queue_push(queue, rq);
+#endif
+                        if (is_done) {  // Boat.__init__  boat_env.py:144-201
+#pragma unroll
+                            for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
+                            stage_reset_obs<T>(c, row, (T)0);  // only experiment 2 starts off the centre line (:166-167)
+                            store_vecs<T, D_COUNT>(gb, lane, d);
+                            st_state(reinterpret_cast<uint2 *>(gb + c.off_idx) + lane, make_uint2(0u, rq.episode));
+                        }
+                    }
+                }
+                unsigned todo = kSetup > 0 ? 0u : __ballot_sync(FULL, need_setup && active && (!is_done || auto_reset));
                 while (todo) {
                     const int src = __ffs(todo) - 1;
                     todo &= todo - 1;
@@ -573,7 +693,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                             stage_reset_obs<T>(c, row, sy0);
                             if (!KMULTI) {
                                 store_vecs<T, D_COUNT>(gb, lane, d);
-                                __stcs(reinterpret_cast<uint2 *>(gb + c.off_idx) + lane, make_uint2(0u, e_epi));
+                                st_state(reinterpret_cast<uint2 *>(gb + c.off_idx) + lane, make_uint2(0u, e_epi));
                             }
                         }
                     }
@@ -620,6 +740,13 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
         } else {
             __syncwarp();
             for (int e = lane; e < rows * kObsDim; e += 32) gobs[e] = tile[e];
+        }
+    }
+    if (kSetup > 0) {
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            atomicAdd(&queue->producers_done, 1u);
         }
     }
     if (tile_in_flight && lane == 0) tma_store_wait_all();  // smem must stay valid until the last store has read it

@@ -16,14 +16,16 @@ static inline unsigned grid_for(long long n, int block) { return (unsigned)((n +
 template <int WK, bool KMULTI>
 static cudaError_t launch_step_wk(const DevCfg &c, const StepArgs &a, cudaStream_t st) {
     auto kern = boat_step_kernel<REAL, WK, KMULTI>;
-    const int smem = kWarpsPerCta * WarpSmem<REAL>(c.block_bytes, c.ncurves, c.npieces).bytes;
+    constexpr int n_setup = setup_warps<WK, KMULTI>();
+    constexpr int threads = kTile + 32 * n_setup;
+    const int smem = CtaSmem<REAL>(c.block_bytes, c.ncurves, c.npieces, n_setup).bytes;
     static int cached_smem = -1, ctas_per_sm = 0, n_sm = 0, cached_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (cached_smem != smem || cached_dev != dev) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kTile, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, threads, smem);
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
@@ -35,7 +37,7 @@ static cudaError_t launch_step_wk(const DevCfg &c, const StepArgs &a, cudaStream
     long long grid = (nblk + kWarpsPerCta - 1) / kWarpsPerCta;
     const long long resident = (long long)n_sm * ctas_per_sm;
     if (grid > resident) grid = resident;
-    kern<<<(unsigned)grid, kTile, smem, st>>>(c, a);
+    kern<<<(unsigned)grid, threads, smem, st>>>(c, a);
     return cudaGetLastError();
 }
 
