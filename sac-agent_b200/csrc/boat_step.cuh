@@ -538,12 +538,13 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
 
         T rsum = (T)0;
         int code = BOATENV_TERM_NONE, nsteps = 0;
-        bool alive = true, wind_dirty = false, next_stored = false;
-        if (tile_in_flight) {  // the previous block's observation bulk store must be done reading `tile`
+        bool alive = true, wind_dirty = false;
+        if (tile_in_flight) {  // the previous block's bulk stores must be done reading `tile`
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
             tile_in_flight = false;
         }
+        bool ring_in_flight = false;
         char *gb = c.state + (size_t)blk * (size_t)bb;
 
         // state + per-env outputs of this launch (K = 1: right after the sub-step; K > 1: after the loop)
@@ -615,8 +616,60 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                 }
             }
             if (!KMULTI) store_results();
+            if (!KMULTI && a.rp.state) {
+                // ---- fused agent.remember (main.py:83-88, buffer.py:13-22): the transition leaves while the
+                // tile still holds the TERMINAL observations (a reset below overwrites the rows of finished
+                // envs).  The 32 ring slots of a warp are contiguous (mod mem_size).
+                __syncwarp();
+                const int rows_w = min(32, n_end - blk * 32);
+                long long slot0 = a.rp.base_slot + (long long)blk * 32;
+                if (slot0 >= a.rp.mem_size) slot0 -= a.rp.mem_size;
+                const T *prev = reinterpret_cast<const T *>(a.obs_in) + (size_t)blk * (32 * kObsDim);
+                T *ring_s = reinterpret_cast<T *>(a.rp.state) + slot0 * kObsDim;
+                T *ring_n = reinterpret_cast<T *>(a.rp.new_state) + slot0 * kObsDim;
+                const bool bulk = rows_w == 32 && slot0 + 32 <= a.rp.mem_size &&
+                                  ((reinterpret_cast<uintptr_t>(ring_s) | reinterpret_cast<uintptr_t>(ring_n)) & 15u) == 0;
+                if (bulk) {  // s' = the staged tile: one bulk store; s = last step's observation tile: 128-bit copy
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_1d(ring_n, tile, kTileBytes);
+                        tma_store_commit();
+                    }
+                    ring_in_flight = true;
+                    using V = typename VecOf<T>::type;
+                    constexpr int NVEC = 32 * kObsDim / VecOf<T>::W;
+                    const V *pv = reinterpret_cast<const V *>(prev);
+                    V *rs = reinterpret_cast<V *>(ring_s);
+#pragma unroll
+                    for (int it = 0; it < (NVEC + 31) / 32; ++it) {
+                        const int v = lane + 32 * it;
+                        if (v < NVEC) rs[v] = __ldcs(pv + v);
+                    }
+                } else {
+                    for (int e = lane; e < rows_w * kObsDim; e += 32) {
+                        const int rr = e / kObsDim, q = e - rr * kObsDim;
+                        long long slot = a.rp.base_slot + (long long)blk * 32 + rr;
+                        if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
+                        reinterpret_cast<T *>(a.rp.state)[slot * kObsDim + q] = prev[e];
+                        reinterpret_cast<T *>(a.rp.new_state)[slot * kObsDim + q] = tile[e];
+                    }
+                }
+                if (active) {
+                    long long slot = a.rp.base_slot + i;
+                    if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
+                    reinterpret_cast<T *>(a.rp.action)[slot] = action;
+                    reinterpret_cast<T *>(a.rp.reward)[slot] = rsum;
+                    a.rp.terminal[slot] = a.rp.done_flag_mode ? (code == BOATENV_TERM_REACHED_GOAL) : (code != BOATENV_TERM_NONE);
+                }
+            }
             // ---- slow path: the warp serves its lanes one at a time ----
             if (__ballot_sync(FULL, need_setup && active)) {
+                if (ring_in_flight) {  // the bulk store of s' must have read the tile before rows are reset
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                    ring_in_flight = false;
+                }
                 const bool is_done = need_setup && active && code != BOATENV_TERM_NONE;
                 if (is_done) {  // statistics (info dict, boat_env.py:24-32,87-113): sparse events -> per-env REDs
                     double *cnt = c.counters + (blk & (kCounterSlots - 1)) * 32;
@@ -631,14 +684,6 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                         T *fo = reinterpret_cast<T *>(a.final_obs_out) + (size_t)i * kObsDim;
 #pragma unroll
                         for (int q = 0; q < kObsDim; ++q) fo[q] = row[q];
-                    }
-                    if (a.rp.state) {  // s' of the fused store_transition (buffer.py:16)
-                        long long slot = a.rp.base_slot + i;
-                        if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
-                        T *s1 = reinterpret_cast<T *>(a.rp.new_state) + slot * kObsDim;
-#pragma unroll
-                        for (int q = 0; q < kObsDim; ++q) s1[q] = row[q];
-                        next_stored = true;
                     }
                 }
                 if (kSetup > 0) {
@@ -704,27 +749,6 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
         if (KMULTI) store_results();
 
         const int rows = min(32, n_end - blk * 32);
-        if (a.rp.state) {  // fused store_transition  buffer.py:13-22: ring slots of a warp are contiguous (mod size)
-            __syncwarp();  // the warp's staging tile is complete
-            const unsigned skip = __ballot_sync(FULL, next_stored);
-            const T *prev = reinterpret_cast<const T *>(a.obs_in) + (size_t)blk * (32 * kObsDim);
-            T *ring_s = reinterpret_cast<T *>(a.rp.state), *ring_n = reinterpret_cast<T *>(a.rp.new_state);
-            for (int e = lane; e < rows * kObsDim; e += 32) {
-                const int rr = e / kObsDim, q = e - rr * kObsDim;
-                long long slot = a.rp.base_slot + blk * 32 + rr;
-                if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
-                ring_s[slot * kObsDim + q] = prev[e];
-                if (!((skip >> rr) & 1u)) ring_n[slot * kObsDim + q] = tile[e];
-            }
-            if (active) {
-                long long slot = a.rp.base_slot + i;
-                if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
-                reinterpret_cast<T *>(a.rp.action)[slot] = action;
-                reinterpret_cast<T *>(a.rp.reward)[slot] = rsum;
-                a.rp.terminal[slot] = a.rp.done_flag_mode ? (code == BOATENV_TERM_REACHED_GOAL) : (code != BOATENV_TERM_NONE);
-            }
-            // prev rows are read before the copy-out below overwrites them (obs_in may alias obs_out)
-        }
         // ---- observations: the [rows][11] tile is contiguous in obs_out -> one bulk store ----
         T *gobs = reinterpret_cast<T *>(a.obs_out) + (size_t)blk * (32 * kObsDim);
         if (rows == 32) {

@@ -190,6 +190,31 @@ def test_cuda_vs_oracle_seeded(S, O, experiment, precision, n, T):
     env.close()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_synchronised_piece_crossings_flood_the_setup_queue(S, O, precision):
+    """Worst case for the warp-specialised K = 1 kernel: t_max = 60 s gives L = 240 wind samples, i.e. a
+    new spline piece every ~34 steps, and with tiny actions nobody resets, so EVERY env of every warp asks
+    for new wind coefficients in the same launch -- 8 x 32 requests per CTA against a 64-slot ring (the
+    producers block until the setup warps have drained it).  Timeouts then reset everybody at once."""
+    cfg = S.load_config(base_settings__experiment=6, base_settings__t_max=60)
+    n, T, E = 40_000, 300, 3
+    env = make_env(S, cfg, n, precision, seed=21, auto_reset=True)
+    s_y, knots = host_draws(env, E)
+    env.reset()
+    import torch
+    actions = np_(torch.stack([env.uniform_actions(t, 0.01).clone() for t in range(T)]))
+    ref = O.rollout(O.params_from_config(cfg), actions, s_y, knots, auto_reset=True)
+    out = run_steps(env, actions)
+    assert np.array_equal(out["done"], ref["done"]) and np.array_equal(out["term"], ref["term"])
+    assert (ref["term"] == 4).sum() == n  # everybody times out at step 240, together
+    tol = TOL64 if precision == "fp64" else TOL32
+    d = ref["done"].astype(bool)
+    assert scaled_err(out["obs"][~d], ref["obs"][~d]).max() <= tol
+    assert scaled_err(out["final_obs"][d], ref["obs"][d]).max() <= tol
+    assert scaled_err(out["reward"], ref["reward"]).max() <= tol
+    env.close()
+
+
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
 def test_auto_reset_matches_oracle(S, O, precision):
     """Uniform(-1,1) policy A1: episodes end by rudder_broken every ~360 steps; the kernel
