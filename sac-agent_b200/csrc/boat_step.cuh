@@ -364,9 +364,13 @@ __device__ __forceinline__ bool queue_pop(SetupQueue *q, int n_producers, SetupR
     const unsigned s = ticket % kQueueSlots;
     volatile unsigned *seq = q->seq + s;
     volatile unsigned *done = &q->producers_done, *tail = &q->tail;
+    // Nobody waits for the coefficients before the NEXT launch, so an idle consumer sleeps long (up to
+    // ~1 us per poll) instead of burning issue slots and power next to the streaming warps.
+    unsigned backoff = 128u;
     while (*seq != ticket + 1u) {
         if (*done == (unsigned)n_producers && (int)(ticket - *tail) >= 0) return false;
-        __nanosleep(128);
+        __nanosleep(backoff);
+        backoff = min(backoff * 2u, 1024u);
     }
     __threadfence_block();
     r = q->slot[s];
