@@ -256,7 +256,6 @@ int boatenv_create(const boatenv_params *params, int64_t n_envs, uint64_t seed, 
     cfg.n_envs = n_envs;
     cfg.env_id_offset = env_id_offset;
     cfg.seed = seed;
-    const size_t n = (size_t)n_envs;
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     {   // tile-blocked state: [dyn][idx][wind A][wind B] sections per 32-env block (common.cuh)

@@ -239,27 +239,6 @@ __device__ __forceinline__ void stage_reset_obs(const DevCfg &c, T *row, T s_y0)
     row[10] = (T)1;
 }
 
-// Coalesced write of a warp's [rows][11] staging tile to rows [row0, row0 + rows) of a
-// row-major [n][11] global tensor: 128-bit stores of the contiguous 32 x 11 block.
-template <typename T>
-__device__ __forceinline__ void copy_out_tile(const T *tile, T *gout, long long row0, int rows, int lane) {
-    using V = typename VecOf<T>::type;
-    constexpr int W = VecOf<T>::W;
-    constexpr int NVEC = 32 * kObsDim / W;
-    T *g = gout + row0 * kObsDim;
-    if (rows == 32 && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
-        V *gv = reinterpret_cast<V *>(g);
-        const V *sv = reinterpret_cast<const V *>(tile);
-#pragma unroll
-        for (int it = 0; it < (NVEC + 31) / 32; ++it) {
-            const int v = lane + 32 * it;
-            if (v < NVEC) __stcs(gv + v, sv[v]);
-        }
-    } else {
-        for (int e = lane; e < rows * kObsDim; e += 32) g[e] = tile[e];
-    }
-}
-
 // ---------------------------------------------------------------------------------
 // TMA bulk-copy + mbarrier primitives (sm_90+/sm_100a PTX).  The copies are 1-D
 // (cp.async.bulk, no tensor map): a warp's state block is contiguous in HBM.
@@ -286,18 +265,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// global -> shared bulk copy, completion counted in bytes on `bar`.  Default L2 policy: measured 3 % faster
-// than an evict_first hint (BOAT_LOAD_EVICT_FIRST), the alternating sweep lets the tail of a launch hit L2.
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar,
-                                            uint64_t policy) {
-#ifndef BOAT_LOAD_EVICT_FIRST
+// global -> shared bulk copy, completion counted in bytes on `bar`.  Default L2 policy: an evict_first
+// cache hint measured 3 % slower (the alternating sweep lets the tail of a launch hit L2 in the next one).
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
                      "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-#else
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
-            "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
-#endif
 }
 // shared -> global bulk copy (bulk async-group completion)
 __device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
@@ -310,12 +282,9 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy writes (st.shared) -> visible to the async proxy (the bulk store that follows)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-
+// Build-time switches.  BOAT_MINBLOCKS_F32 / BOAT_STAGES / BOAT_SETUP_WARPS / BOAT_CTA_THREADS are tuning
+// knobs (defaults = measured optimum); the BOAT_DEBUG_* macros remove parts of the kernel for the
+// ablation measurements quoted in DESIGN.md section 4 and are never defined in a product build.
 #ifndef BOAT_MINBLOCKS_F32
 #define BOAT_MINBLOCKS_F32 2  // 256-thread CTAs per SM the fp32 kernel is register-budgeted for
 #endif
@@ -483,7 +452,6 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
     }
     auto block_of = [&](int q) { return rev ? (blk_last - (q - blk_first)) : q; };
 
-    const uint64_t pol = policy_evict_first();
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
@@ -496,7 +464,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             const int q = seq + s * wstride;
             if (q < blk_end) {
                 mbar_expect_tx(full + s, (uint32_t)bb);
-                tma_load_1d(stage_base + s * bb, c.state + (size_t)block_of(q) * (size_t)bb, (uint32_t)bb, full + s, pol);
+                tma_load_1d(stage_base + s * bb, c.state + (size_t)block_of(q) * (size_t)bb, (uint32_t)bb, full + s);
             }
         }
     }
@@ -535,7 +503,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             const int q = seq + kStages * wstride + (int)(ix.x >> 31);
             if (q < blk_end) {
                 mbar_expect_tx(full + stage, (uint32_t)bb);
-                tma_load_1d(stage_base + stage * bb, c.state + (size_t)block_of(q) * (size_t)bb, (uint32_t)bb, full + stage, pol);
+                tma_load_1d(stage_base + stage * bb, c.state + (size_t)block_of(q) * (size_t)bb, (uint32_t)bb, full + stage);
             }
         }
         if (++stage == kStages) { stage = 0; parity ^= 1u; }
