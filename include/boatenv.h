@@ -160,6 +160,18 @@ BOATENV_API int boatenv_set_episode_draws(boatenv_t h, const int32_t *s_y_start,
 BOATENV_API int boatenv_episode_draws_host(const boatenv_params *params, uint64_t seed, int64_t global_env_id,
                                uint32_t episode, int32_t *s_y_start_out, double *knots_out);
 
+/* ---- checkpoint / resume ----------------------------------------------------------- */
+
+/* The reference checkpoints network weights only (networks/base_network.py:13-17); env state is
+ * lost on restart.  Here the complete env state (all per-env scalars, step / episode indices,
+ * wind coefficients, the cumulative statistics) is one opaque device blob: together with the
+ * counter-based Philox streams it makes resume exact.  boatenv_state_bytes gives its size;
+ * export / import copy it to / from a caller-owned device buffer.  A blob is only valid for a
+ * handle created with the same params, n_envs and precision. */
+BOATENV_API int64_t boatenv_state_bytes(boatenv_t h);
+BOATENV_API int boatenv_export_state(boatenv_t h, void *blob_out, void *stream);
+BOATENV_API int boatenv_import_state(boatenv_t h, const void *blob_in, void *stream);
+
 /* ---- statistics (info dict of boat_env.py:24-32, cumulative) ----------------------- */
 
 /* out_host[8] = { reached_goal, out_of_bounds, out_of_fuel, timeout, rudder_broken,

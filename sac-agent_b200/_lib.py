@@ -45,6 +45,9 @@ SIGNATURES = {
     "boatenv_wind_length": (C.c_int, [vp]),
     "boatenv_set_episode_draws": (C.c_int, [vp, vp, vp, vp]),
     "boatenv_episode_draws_host": (C.c_int, [PP, u64, i64, u32, C.POINTER(i32), C.POINTER(dbl)]),
+    "boatenv_state_bytes": (i64, [vp]),
+    "boatenv_export_state": (C.c_int, [vp, vp, vp]),
+    "boatenv_import_state": (C.c_int, [vp, vp, vp]),
     "boatenv_get_counters": (C.c_int, [vp, C.POINTER(dbl), vp]),
     "boatenv_reduce_counters": (C.c_int, [vp, vp, vp]),
     "boatenv_fill_uniform_actions": (C.c_int, [vp, u64, dbl, vp, vp]),

@@ -208,6 +208,32 @@ class BatchedBoatEnv:
                                                       C.byref(s), k), "boatenv_episode_draws_host")
         return int(s.value), np.array(k[:], dtype=np.float64).reshape(2, fp)
 
+    # -- checkpoint / resume -----------------------------------------------------------
+    def state_dict(self):
+        """Everything needed to resume this population exactly: the opaque device state blob (per-env
+        scalars, step / episode indices, wind coefficients, cumulative statistics) plus the host-side
+        identity of the handle.  The Philox streams are counter-based, so nothing else is stateful."""
+        torch = _torch()
+        blob = torch.empty(int(self._L.boatenv_state_bytes(self._h)), dtype=torch.uint8, device=self.device)
+        _lib.check(self._L.boatenv_export_state(self._h, blob.data_ptr(), self._stream()), "boatenv_export_state")
+        return {"blob": blob, "obs": self.obs.clone(), "n_envs": self.n_envs, "precision": self.precision,
+                "seed": self.seed, "env_id_offset": self.env_id_offset,
+                "params": bytes(memoryview(self.params).cast("B"))}
+
+    def load_state_dict(self, sd):
+        torch = _torch()
+        for k in ("n_envs", "precision", "seed", "env_id_offset"):
+            if sd[k] != getattr(self, k):
+                raise ValueError(f"checkpoint {k}={sd[k]!r} does not match this env ({getattr(self, k)!r})")
+        if sd["params"] != bytes(memoryview(self.params).cast("B")):
+            raise ValueError("checkpoint was taken with a different config")
+        blob = sd["blob"].to(self.device).contiguous()
+        if blob.numel() != int(self._L.boatenv_state_bytes(self._h)):
+            raise ValueError("checkpoint blob has the wrong size")
+        _lib.check(self._L.boatenv_import_state(self._h, blob.data_ptr(), self._stream()), "boatenv_import_state")
+        self.obs.copy_(sd["obs"])
+        torch.cuda.current_stream(self.device).synchronize()
+
     def counters(self):
         out = (C.c_double * 8)()
         _lib.check(self._L.boatenv_get_counters(self._h, out, self._stream()), "boatenv_get_counters")

@@ -505,6 +505,35 @@ int boatenv_episode_draws_host(const boatenv_params *params, uint64_t seed, int6
     return BOATENV_OK;
 }
 
+static size_t state_block_bytes(boatenv_t h) { return (size_t)num_blocks(h->cfg.n_envs) * (size_t)h->cfg.block_bytes; }
+static size_t counter_bytes() { return (size_t)kCounterSlots * 32 * sizeof(double); }
+
+int64_t boatenv_state_bytes(boatenv_t h) {
+    return h ? (int64_t)(state_block_bytes(h) + counter_bytes()) : (int64_t)BOATENV_EINVAL;
+}
+
+int boatenv_export_state(boatenv_t h, void *blob_out, void *stream) {
+    if (!h || !blob_out) return BOATENV_EINVAL;
+    if (!h->was_reset) return BOATENV_ESTATE;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(blob_out, h->cfg.state, state_block_bytes(h), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync((char *)blob_out + state_block_bytes(h), h->cfg.counters, counter_bytes(),
+                             cudaMemcpyDeviceToDevice, st));
+    return BOATENV_OK;
+}
+
+int boatenv_import_state(boatenv_t h, const void *blob_in, void *stream) {
+    if (!h || !blob_in) return BOATENV_EINVAL;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(h->cfg.state, blob_in, state_block_bytes(h), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->cfg.counters, (const char *)blob_in + state_block_bytes(h), counter_bytes(),
+                             cudaMemcpyDeviceToDevice, st));
+    h->was_reset = true;
+    return BOATENV_OK;
+}
+
 int boatenv_reduce_counters(boatenv_t h, double *out_device, void *stream) {
     if (!h || !out_device) return BOATENV_EINVAL;
     CUDA_TRY(cudaSetDevice(h->device));

@@ -7,6 +7,8 @@ rewards within 1e-9 (fp64 validation mode) and 1e-4 (fp32 production mode) over 
 steps, measured as |a-b| / max(|b|, S_i) on the reference's own normalised observations
 (S_i = 1).
 """
+import json
+
 import numpy as np
 import pytest
 
@@ -432,3 +434,76 @@ def test_full_size_properties(S):
         env.close()
     assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
     assert runs[0][2]["episodes"] == runs[1][2]["episodes"]
+
+
+def test_checkpoint_resume_is_exact(S, tmp_path):
+    """the reference saves only network weights; here the env state is one blob and
+    Philox is counter-based, so save -> keep running == restore -> run again, bit for bit (incl. statistics)."""
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    n = 50_000
+    env = make_env(S, cfg, n, "fp32", seed=13, auto_reset=True)
+    env.reset()
+    for t in range(150):
+        env.step(env.uniform_actions(t, 2.0))
+    sd = env.state_dict()
+    torch.save(sd, tmp_path / "env.pt")
+    tail_a = []
+    for t in range(150, 300):
+        o, r, d, info = env.step(env.uniform_actions(t, 2.0))
+        tail_a.append((o.clone(), r.clone(), d.clone(), info["term"].clone()))
+    ca = env.counters()
+    twin = make_env(S, cfg, n, "fp32", seed=13, auto_reset=True)   # a fresh process would do exactly this
+    twin.load_state_dict(torch.load(tmp_path / "env.pt"))
+    assert torch.equal(twin.obs, sd["obs"])
+    for t, (o, r, d, tm) in zip(range(150, 300), tail_a):
+        o2, r2, d2, info2 = twin.step(twin.uniform_actions(t, 2.0))
+        assert torch.equal(o2, o) and torch.equal(r2, r) and torch.equal(d2, d) and torch.equal(info2["term"], tm)
+    cb = twin.counters()
+    assert ca["episodes"] == cb["episodes"] > 0 and ca["rudder_broken"] == cb["rudder_broken"]
+    assert cb["return_sum"] == pytest.approx(ca["return_sum"], rel=1e-9)
+    other = make_env(S, cfg, n, "fp32", seed=14)
+    with pytest.raises(ValueError):
+        other.load_state_dict(sd)
+    for e in (env, twin, other):
+        e.close()
+
+
+def test_recorder_compatible_export(S, tmp_path):
+    """the CSVs of postprocessing/recorder.py from a GPU run.  Replaying fixture 6
+    (test_mode 1) and reading the files back the way the reference's Replayer does (pandas, sep=';')
+    reproduces the recorded episode_0_data.csv / wind.csv / info.csv."""
+    import pandas as pd
+    import torch
+    g = load_golden("fixture_exp6")
+    fp = int(g["config"]["wind"]["fixed_points"])
+    knots = np.zeros((1, 2, fp))
+    knots[0, 0], knots[0, 1] = g["knots_v"], g["knots_a"]
+    env = make_env(S, g["config"], 1, "fp64", np.array([0]), knots, auto_reset=True)
+    env.reset()
+    rec = S.BatchedRecorder(env, [0], str(tmp_path))
+    rec.write_winds_to_csv()
+    zero = torch.zeros(1, dtype=env.dtype, device=env.device)
+    done = False
+    while not done:
+        rec.write_data_to_csv()
+        _, _, d, _ = env.step(zero)
+        rec.after_step(zero)
+        done = bool(d[0])
+    data = pd.read_csv(tmp_path / "episodes" / "episode_0_data.csv", sep=";")
+    assert list(data.columns) == json.loads('["boat_position_x", "boat_position_y", "boat_velocity_x", "boat_velocity_y", '
+                                            '"boat_angle", "action_rudder", "reward", "rudder_angle", "n"]')
+    assert len(data) == int(g["n_rows"])
+    rows = data.values[g["row_idx"]]
+    ref = g["rows"]
+    for col, scale in ((0, 3900.0), (1, 800.0), (2, 5.0), (3, 2.0), (4, 2 * np.pi)):
+        assert scaled_err(rows[:, col], ref[:, col], scale).max() <= 1e-11
+    m = g["row_idx"] > 0
+    assert np.abs(rows[m, 6] - ref[m, 6]).max() <= 1e-11 and np.all(rows[:, 8] == 20)
+    wind = pd.read_csv(tmp_path / "episodes" / "wind.csv", sep=";")
+    assert list(wind.columns) == ["wind_velocity", "wind_angle"] and len(wind) == 10000
+    assert np.abs(wind.wind_velocity.values[g["wind_idx"]] - g["wind_v"]).max() < 5e-14
+    info = pd.read_csv(tmp_path / "episodes" / "info.csv", sep=";")
+    assert info.termination[0] == "reached_goal" and info.reached_goal[0] == 1
+    assert info.episode_reward[0] == pytest.approx(871.2727580297085, abs=1e-8)
+    env.close()
