@@ -95,7 +95,7 @@ class SAC:
         with torch.no_grad():  # Polyak average of the target value net (continuous_agent.py:66-80)
             for p, pt in zip(self.v.parameters(), self.v_targ.parameters()):
                 pt.mul_(1.0 - self.tau).add_(p, alpha=self.tau)
-        return float(v_loss), float(actor_loss), float(q_loss)
+        return v_loss.item(), actor_loss.item(), q_loss.item()
 
 
 def main(argv=None):
