@@ -123,7 +123,8 @@ BOATENV_API int boatenv_step_k(boatenv_t h, const void *actions, int64_t action_
 
 /* The same step through HOST buffers (pinned or pageable): copies actions H2D, steps,
  * copies obs/reward/done D2H, chunked over internal streams so that the copies overlap
- * the kernel.  Blocks until the results are in host memory.  This is the end-to-end
+ * the kernel.  Waits for all work queued on the device before it starts and blocks until
+ * the results are in host memory.  This is the end-to-end
  * call a CPU-side agent loop (main.py:80-81) makes. */
 BOATENV_API int boatenv_step_host(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host,
                       uint8_t *done_host, uint32_t flags);

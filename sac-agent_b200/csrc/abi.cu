@@ -406,6 +406,9 @@ int boatenv_step_host(boatenv_t h, const void *actions_host, void *obs_host, voi
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = ensure_host_path(h);
     if (rc) return rc;
+    // The copies and launches below run on the handle's own streams: order them after whatever the
+    // caller has queued on this device (a reset / step on its stream) -- this call is blocking anyway.
+    CUDA_TRY(cudaDeviceSynchronize());
     const long long n = h->cfg.n_envs;
     // chunks are multiples of the CTA tile so that every tile keeps its 16-byte alignment
     int nchunks = n >= 8LL * 65536 ? 8 : (n >= 4LL * 65536 ? 4 : 1);
