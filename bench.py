@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "batched BoatEnv env-steps/sec"
+METRIC = "batched BoatEnv env-steps/sec at 1/2/4/8 B200; % of HBM roofline"  # BASELINE.json "metric", verbatim
 UNIT = "env-steps/s"
 ENVS_PER_GPU = 16_777_216
 EXPERIMENT = 6
@@ -223,6 +223,7 @@ def run_ours(args) -> None:
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = S.sharding.bind_to_gpu_numa_node(local_rank) if world > 1 else []
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = S.lib()
@@ -326,7 +327,8 @@ def run_ours(args) -> None:
                              "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP,
                              "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * n_local, "peak_source": peak_src},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "api": "BatchedBoatEnv.step_host (boatenv_step_host, pinned host buffers)"},
+                        "steps": e2e_steps, "api": "BatchedBoatEnv.step_host (boatenv_step_host, pinned host buffers)",
+                        "rank0_cpu_affinity": len(numa_cpus) or None},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "episodes_finished": counters["episodes"], "mean_episode_return": counters["return_mean"]}
         if not args.no_cpu_baseline:

@@ -5,12 +5,25 @@ access, and every entry point here also accepts a real DotMap or a plain dict.
 """
 from __future__ import annotations
 
+import copy
 import ctypes as C
-import os
 
 import yaml
 
-DEFAULT_CONFIG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "original_config.yaml")
+# The values the hot path reads, with the defaults the reference ships in configs/original_config.yaml
+# (:7-9 base settings, :25-27 track, :32-54 boat model, :63-65 wind), plus the `agent:` block
+# (:13-22) that the SAC example uses.  Keys the env never reads (n_games,
+# render_skip_size, boat.n_max/w/aspect_ratio/a/b, agent.layer*_size) are not carried.
+DEFAULTS = {
+    "base_settings": {"test_mode": 0, "dt": 0.25, "t_max": 2500, "experiment": 5},
+    "boat_env": {"track_width": 800, "boat_out_of_bounds_offset": 0, "goal_line": 3900},
+    "boat": {"fuel": 15000, "boat_m": 600, "boat_m_x": 50, "boat_m_y": 100, "boat_I": 6_000_000, "boat_Iz": 10,
+             "propeller_diameter": 1, "wake_friction": 0.3, "c_r_front": 0.31, "c_r_side": 2, "thrust_deduction": 0.3,
+             "rho": 1, "boat_area_front": 20, "boat_area_side": 90, "boat_l": 15, "boat_b": 6, "rudder_area": 10},
+    "wind": {"fixed_points": 8, "max_velocity": 0.5, "direction": 90},
+    "agent": {"learning_rate_alpha": 0.005, "learning_rate_beta": 0.0003, "gamma": 0.99,
+              "tvn_parameter_modulation_tau": 0.005, "max_size": 1_000_000, "batch_size": 1024, "reward_scale": 10},
+}
 
 
 class AttrDict(dict):
@@ -29,9 +42,14 @@ class AttrDict(dict):
 
 
 def load_config(path: str | None = None, **overrides) -> AttrDict:
-    """get_config (utils/config_reader.py:6-8).  ``overrides``: section__key=value."""
-    with open(path or DEFAULT_CONFIG) as f:
-        cfg = yaml.safe_load(f)
+    """get_config (utils/config_reader.py:6-8): a reference YAML (original_config.yaml,
+    tuned_configs.yaml) is read unchanged; without a path the defaults above are used.
+    ``overrides``: section__key=value."""
+    if path is None:
+        cfg = copy.deepcopy(DEFAULTS)
+    else:
+        with open(path) as f:
+            cfg = yaml.safe_load(f)
     for k, v in overrides.items():
         sec, key = k.split("__", 1)
         cfg[sec][key] = v

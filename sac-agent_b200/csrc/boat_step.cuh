@@ -445,7 +445,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
     const int wstride = (int)gridDim.x * kWarpsPerCta;
     const int blk_first = (int)(a.env_begin >> 5), blk_last = blk_end - 1;
     const bool rev = a.reverse != 0;
-    int seq = blk_first + (int)blockIdx.x * kWarpsPerCta + warp;
+    int seq = blk_first + (int)blockIdx.x * kWarpsPerCta + warp;  // CTA-major: 8 consecutive blocks per CTA (warp-major measured 2 % slower)
     if (seq >= blk_end) {
         if (kSetup > 0 && lane == 0) atomicAdd(&queue->producers_done, 1u);
         return;

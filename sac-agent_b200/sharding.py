@@ -49,3 +49,26 @@ def make_sharded_env(config, n_total: int, seed: int = 0, precision: str = "fp32
     offset, n_local = shard_range(n_total, rank, world)
     return BatchedBoatEnv(config, n_local, seed=seed, precision=precision, device=local_rank,
                           env_id_offset=offset, auto_reset=auto_reset)
+
+
+def bind_to_gpu_numa_node(cuda_index: int) -> list[int]:
+    """Pin this process to the CPUs NVML reports as local to its GPU, so that pinned host buffers
+    allocated afterwards (first touch) and the threads that drive the copies sit on the GPU's NUMA
+    node.  Matters for the host-buffer path (``step_host``) when 8 ranks share one host.  Returns the
+    CPU list (empty if NVML or the affinity call is unavailable -- then nothing changes)."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(cuda_index)
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return []

@@ -78,7 +78,8 @@ def test_missing_library_fails_loudly(S, monkeypatch):
 
 
 def test_config_semantics(S):
-    """original_config.yaml is accepted unchanged; only the hot-path keys are read."""
+    """A reference YAML (original_config.yaml) is accepted unchanged; only the hot-path keys are read;
+    the built-in defaults equal the reference's shipped values."""
     ref_cfg = "/root/reference/configs/original_config.yaml"
     cfg = S.load_config()
     p = S.params_from_config(cfg)
@@ -91,6 +92,8 @@ def test_config_semantics(S):
         q = S.params_from_config(theirs)
         for name, _ in p._fields_:
             assert getattr(p, name) == getattr(q, name), name
+        r = S.params_from_config(S.load_config(ref_cfg))  # the file itself, read by our loader
+        assert bytes(memoryview(r).cast("B")) == bytes(memoryview(q).cast("B"))
     # plain dicts and attribute containers both work (the reference passes a DotMap)
     assert S.params_from_config(dict(cfg)).boat_m == p.boat_m
     assert cfg.base_settings.experiment == cfg["base_settings"]["experiment"]
