@@ -187,7 +187,7 @@ def run_reference(args) -> None:
     total = max(1, args.steps + args.warmup)
     steps, dt = port.sample(16 * cores, t_steps)
     rate = steps / dt
-    budget = 90.0 / total                                  # seconds per bench "step"
+    budget = args.ref_budget_s / total                     # seconds per bench "step"
     n_envs = int(max(cores, min(rate * budget / t_steps, 65536)))
     for _ in range(args.warmup):
         port.sample(n_envs, t_steps)
@@ -351,6 +351,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-timed part only (for ncu runs)")
     ap.add_argument("--action-scale", type=float, default=1.0, help="experiments only: scale of the uniform policy")
+    ap.add_argument("--ref-budget-s", type=float, default=90.0, help="--impl reference: CPU seconds for all steps together")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps
