@@ -4,6 +4,7 @@
 // five parallel arrays state[size][obs], new_state[size][obs], action[size][na],
 // reward[size], terminal[size] -- so a sampled batch is five dense tensors the
 // learner can consume without a transpose.
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -36,36 +37,39 @@ struct boatreplay_handle {
 
 namespace {
 
-// store_transition (buffer.py:13-22) for n rows: flat element e of the [n][width] input
-// goes to ring slot (cntr + e / width) % size.  Consecutive threads write consecutive
-// addresses except at the single wrap point.
+// store_transition (buffer.py:13-22) for a run of rows whose ring slots are CONTIGUOUS (the host splits
+// a batch at the wrap point): five flat copies src[row0 ..] -> ring[slot0 ..].  128-bit path when source
+// and destination of an array are both 16-byte aligned, scalar (still coalesced) otherwise.
+template <typename T>
+__device__ __forceinline__ void copy_flat(T *__restrict__ dst, const T *__restrict__ src, long long count, long long tid,
+                                          long long nthreads) {
+    using V = typename VecOf<T>::type;
+    constexpr int W = VecOf<T>::W;
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
+        const long long nvec = count / W;
+        const V *sv = reinterpret_cast<const V *>(src);
+        V *dv = reinterpret_cast<V *>(dst);
+        for (long long v = tid; v < nvec; v += nthreads) dv[v] = __ldcs(sv + v);
+        for (long long e = nvec * W + tid; e < count; e += nthreads) dst[e] = src[e];
+    } else {
+        for (long long e = tid; e < count; e += nthreads) dst[e] = __ldcs(src + e);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) replay_store_kernel(
     T *__restrict__ state, T *__restrict__ new_state, T *__restrict__ action, T *__restrict__ reward,
     uint8_t *__restrict__ terminal, const T *__restrict__ s, const T *__restrict__ a, const T *__restrict__ r,
-    const T *__restrict__ s2, const uint8_t *__restrict__ done, long long n, long long cntr, long long size,
+    const T *__restrict__ s2, const uint8_t *__restrict__ done, long long rows, long long row0, long long slot0,
     int obs_dim, int n_actions) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    // rows older than the last `size` are overwritten inside this very call: skip them
-    const long long first = n > size ? n - size : 0;
-    for (long long e = tid + first * obs_dim; e < n * obs_dim; e += stride) {
-        const long long row = e / obs_dim;
-        const int q = (int)(e - row * obs_dim);
-        const long long slot = (cntr + row) % size;
-        state[slot * obs_dim + q] = __ldcs(s + e);
-        new_state[slot * obs_dim + q] = __ldcs(s2 + e);
-    }
-    for (long long e = tid + first * n_actions; e < n * n_actions; e += stride) {
-        const long long row = e / n_actions;
-        const int q = (int)(e - row * n_actions);
-        action[((cntr + row) % size) * n_actions + q] = __ldcs(a + e);
-    }
-    for (long long row = tid + first; row < n; row += stride) {
-        const long long slot = (cntr + row) % size;
-        reward[slot] = __ldcs(r + row);
-        terminal[slot] = done[row] ? 1 : 0;  // np.zeros(..., bool) storage (buffer.py:11,20)
-    }
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    copy_flat<T>(state + slot0 * obs_dim, s + row0 * obs_dim, rows * obs_dim, tid, nthreads);
+    copy_flat<T>(new_state + slot0 * obs_dim, s2 + row0 * obs_dim, rows * obs_dim, tid, nthreads);
+    copy_flat<T>(action + slot0 * n_actions, a + row0 * n_actions, rows * n_actions, tid, nthreads);
+    copy_flat<T>(reward + slot0, r + row0, rows, tid, nthreads);
+    for (long long e = tid; e < rows; e += nthreads)
+        terminal[slot0 + e] = done[row0 + e] ? 1 : 0;  // np.zeros(..., bool) storage (buffer.py:11,20)
 }
 
 // np.random.choice(max_mem, batch) stand-in (buffer.py:27): draw b = word (b & 3) of
@@ -80,10 +84,13 @@ __device__ __forceinline__ long long replay_index(unsigned long long seed, unsig
     return (long long)__umul64hi((unsigned long long)w << 32, (unsigned long long)max_mem);
 }
 
-// sample_buffer's gather (buffer.py:29-33).  One thread per output element of the two
-// [batch][obs_dim] tensors; the first `batch` threads also move action/reward/done.
-// USE_IDX: indices supplied by the caller; otherwise drawn in-kernel (and optionally
-// exported through idx_out).
+// sample_buffer's gather (buffer.py:29-33).  A CTA serves kGatherRows consecutive output rows: it first
+// puts their ring indices into shared memory (drawn in-kernel -- one Philox call per 4 rows -- or read
+// from idx_in), then its threads walk the flat [rows][obs_dim] element range of state and new_state
+// (consecutive threads = consecutive output elements: coalesced stores, row-contiguous loads) and the
+// first threads move action / reward / done.
+// USE_IDX: indices supplied by the caller; otherwise drawn in-kernel (and optionally exported).
+constexpr int kGatherRows = 128;
 template <typename T, bool USE_IDX>
 __global__ void __launch_bounds__(256) replay_gather_kernel(
     const T *__restrict__ state, const T *__restrict__ new_state, const T *__restrict__ action,
@@ -91,37 +98,58 @@ __global__ void __launch_bounds__(256) replay_gather_kernel(
     long long *__restrict__ idx_out, T *__restrict__ s_out, T *__restrict__ a_out, T *__restrict__ r_out,
     T *__restrict__ s2_out, uint8_t *__restrict__ d_out, long long batch, long long max_mem, long long size,
     unsigned long long seed, unsigned long long counter, int obs_dim, int n_actions) {
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long e = tid; e < batch * obs_dim; e += stride) {
-        const long long b = e / obs_dim;
-        const int q = (int)(e - b * obs_dim);
-        long long j = USE_IDX ? idx_in[b] : replay_index(seed, counter, b, max_mem);
-        if (USE_IDX) { if (j < 0) j += size; }  // numpy negative indexing
-        s_out[e] = __ldg(state + j * obs_dim + q);
-        s2_out[e] = __ldg(new_state + j * obs_dim + q);
-    }
-    for (long long b = tid; b < batch; b += stride) {
-        long long j = USE_IDX ? idx_in[b] : replay_index(seed, counter, b, max_mem);
-        if (USE_IDX) { if (j < 0) j += size; }
-        for (int q = 0; q < n_actions; ++q) a_out[b * n_actions + q] = __ldg(action + j * n_actions + q);
-        r_out[b] = __ldg(reward + j);
-        d_out[b] = terminal[j];
-        if (!USE_IDX && idx_out) idx_out[b] = j;
+    __shared__ long long jrow[kGatherRows];
+    const int tid = threadIdx.x;
+    for (long long row0 = (long long)blockIdx.x * kGatherRows; row0 < batch; row0 += (long long)gridDim.x * kGatherRows) {
+        const int rows = (int)min((long long)kGatherRows, batch - row0);
+        if (tid < rows) {
+            const long long b = row0 + tid;
+            long long j = USE_IDX ? idx_in[b] : replay_index(seed, counter, b, max_mem);
+            if (USE_IDX && j < 0) j += size;  // numpy negative indexing
+            if (!USE_IDX && idx_out) idx_out[b] = j;
+            jrow[tid] = j;
+        }
+        __syncthreads();
+        const int nelem = rows * obs_dim;
+        T *so = s_out + row0 * obs_dim, *no = s2_out + row0 * obs_dim;
+        for (int e = tid; e < nelem; e += 256) {
+            const int r = e / obs_dim, col = e - r * obs_dim;
+            const long long src = jrow[r] * obs_dim + col;
+            so[e] = __ldg(state + src);
+            no[e] = __ldg(new_state + src);
+        }
+        for (int e = tid; e < rows * n_actions; e += 256) {
+            const int r = e / n_actions, col = e - r * n_actions;
+            a_out[row0 * n_actions + e] = __ldg(action + jrow[r] * n_actions + col);
+        }
+        if (tid < rows) {
+            r_out[row0 + tid] = __ldg(reward + jrow[tid]);
+            d_out[row0 + tid] = terminal[jrow[tid]];
+        }
+        __syncthreads();  // jrow is reused by the next group of rows
     }
 }
 
 template <typename T>
 cudaError_t launch_store(boatreplay_t r, long long n, const void *s, const void *a, const void *rew, const void *s2,
                          const uint8_t *done, cudaStream_t st) {
-    const long long work = n * r->obs_dim;
-    long long blocks = (work + 255) / 256;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
-    replay_store_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
-        (T *)r->state, (T *)r->new_state, (T *)r->action, (T *)r->reward, r->terminal, (const T *)s, (const T *)a,
-        (const T *)rew, (const T *)s2, done, n, r->mem_cntr, r->mem_size, r->obs_dim, r->n_actions);
-    count_launch();
-    return cudaGetLastError();
+    // rows older than the last mem_size are overwritten inside this very call: skip them; then split the
+    // remaining run at the ring's wrap point so that every launch sees contiguous slots
+    long long row0 = n > r->mem_size ? n - r->mem_size : 0;
+    while (row0 < n) {
+        const long long slot0 = (r->mem_cntr + row0) % r->mem_size;
+        const long long rows = std::min(n - row0, r->mem_size - slot0);
+        long long blocks = (rows * r->obs_dim / 4 + 255) / 256;
+        blocks = std::max(1LL, std::min(blocks, 148LL * 8));
+        replay_store_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
+            (T *)r->state, (T *)r->new_state, (T *)r->action, (T *)r->reward, r->terminal, (const T *)s, (const T *)a,
+            (const T *)rew, (const T *)s2, done, rows, row0, slot0, r->obs_dim, r->n_actions);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        row0 += rows;
+    }
+    return cudaSuccess;
 }
 
 template <typename T>
@@ -129,9 +157,8 @@ cudaError_t launch_gather(boatreplay_t r, long long batch, const long long *idx_
                           unsigned long long seed, unsigned long long counter, void *s_out, void *a_out, void *r_out,
                           void *s2_out, uint8_t *d_out, cudaStream_t st) {
     const long long max_mem = r->mem_cntr < r->mem_size ? r->mem_cntr : r->mem_size;
-    const long long work = batch * r->obs_dim;
-    long long blocks = (work + 255) / 256;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    long long blocks = (batch + kGatherRows - 1) / kGatherRows;
+    blocks = std::max(1LL, std::min(blocks, 148LL * 32));
     if (idx_in)
         replay_gather_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(
             (const T *)r->state, (const T *)r->new_state, (const T *)r->action, (const T *)r->reward, r->terminal,
