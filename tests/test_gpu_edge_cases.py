@@ -1,0 +1,168 @@
+"""Edge cases of the batched step path against the oracle: ragged env counts (not a multiple of the
+32-env state block / the 256-thread CTA), the smallest and largest supported spline sizes, very short
+wind tables, stepping past the end of the wind table, unclipped actions, argument errors."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from boat_testlib import scaled_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import sac_agent_b200 as pkg
+    pkg.lib()
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def np_(t):
+    return t.detach().double().cpu().numpy() if t.is_floating_point() else t.detach().cpu().numpy()
+
+
+def rollout_both(S, O, cfg, n, T, precision, scale, auto_reset, episodes, seed=5, k=1):
+    import torch
+    env = S.BatchedBoatEnv(cfg, n, seed=seed, precision=precision, device=0, auto_reset=auto_reset)
+    fp = int(env.params.fixed_points)
+    s_y = np.empty((episodes, n), dtype=np.int32)
+    knots = np.empty((episodes, n, 2, fp))
+    for e in range(episodes):
+        for i in range(n):
+            s_y[e, i], knots[e, i] = env.episode_draws(i, e)
+    env.reset()
+    acts = torch.stack([env.uniform_actions(t, scale).clone() for t in range(T)])
+    ref = O.rollout(O.params_from_config(cfg), np_(acts), s_y, knots, auto_reset=auto_reset)
+    obs = np.empty((T, n, 11)); rew = np.empty((T, n)); done = np.empty((T, n), np.uint8); term = np.empty((T, n), np.uint8)
+    fin = np.zeros((T, n, 11))
+    for t in range(T):
+        o, r, d, info = env.step(acts[t])
+        obs[t], rew[t], done[t], term[t], fin[t] = np_(o), np_(r), np_(d), np_(info["term"]), np_(info["final_obs"])
+    env.close()
+    return ref, dict(obs=obs, reward=rew, done=done, term=term, final_obs=fin)
+
+
+def assert_parity(ref, out, tol, auto_reset):
+    assert np.array_equal(out["done"], ref["done"]) and np.array_equal(out["term"], ref["term"])
+    d = ref["done"].astype(bool)
+    if auto_reset:
+        assert scaled_err(out["obs"][~d], ref["obs"][~d]).max() <= tol
+        if d.any():
+            assert scaled_err(out["final_obs"][d], ref["obs"][d]).max() <= tol
+    else:
+        assert scaled_err(out["obs"], ref["obs"]).max() <= tol
+    assert scaled_err(out["reward"], ref["reward"]).max() <= tol
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 255, 257, 1000])
+@pytest.mark.parametrize("precision,tol", [("fp64", 1e-9), ("fp32", 1e-4)])
+def test_ragged_env_counts(S, O, n, precision, tol):
+    cfg = S.load_config(base_settings__experiment=6, base_settings__t_max=100)  # L = 400: pieces cross every 57 steps
+    ref, out = rollout_both(S, O, cfg, n, 260, precision, 1.0, True, 24)
+    assert_parity(ref, out, tol, True)
+    assert n < 30 or ref["done"].sum() > 0
+
+
+@pytest.mark.parametrize("experiment", [4, 5, 6])
+@pytest.mark.parametrize("fixed_points", [4, 5, 11, 16])
+def test_spline_sizes(S, O, experiment, fixed_points):
+    """wind.fixed_points from the minimum the reference accepts (4, wind.py:73) to this build's maximum (16)."""
+    cfg = S.load_config(base_settings__experiment=experiment, wind__fixed_points=fixed_points,
+                        base_settings__t_max=250)
+    ref, out = rollout_both(S, O, cfg, 96, 400, "fp64", 0.05, True, 4)
+    assert_parity(ref, out, 1e-9, True)
+    env = S.BatchedBoatEnv(cfg, 8, seed=5, precision="fp64", device=0)
+    env.reset()
+    p = O.params_from_config(cfg)
+    for i in (0, 7):  # wind tables == wind.py's for these knots
+        s_y, k = env.episode_draws(i, 0)
+        o = O.OracleEnv(p)
+        o.reset(s_y, k[0], k[1])
+        wv, wa = env.wind_table(i)
+        rv, ra = o.wind()
+        assert np.abs(wv - rv).max() < 1e-13 and np.abs(wa - ra).max() < 1e-12
+    env.close()
+    if fixed_points == 16:
+        with pytest.raises(S.BoatEnvError):   # valid for the reference, unsupported by this build
+            S.BatchedBoatEnv(S.load_config(base_settings__experiment=6, wind__fixed_points=17), 4, device=0)
+
+
+@pytest.mark.parametrize("t_max,dt", [(2.5, 0.25), (9.25, 0.25), (30, 0.5), (3, 0.125)])
+def test_short_wind_tables_and_timeouts(S, O, t_max, dt):
+    """L = int(t_max / dt) as small as 10: every step is a piece crossing; timeout after L steps.
+    (dt must be a binary fraction: with dt = 0.1 the reference's accumulated t falls short of t_max after
+    L steps and its next step indexes past the wind table -- IndexError, wind.py:24.)"""
+    cfg = S.load_config(base_settings__experiment=6, base_settings__t_max=t_max, base_settings__dt=dt)
+    L = int(t_max / dt)
+    ref, out = rollout_both(S, O, cfg, 64, 3 * L + 5, "fp64", 0.02, True, 8)
+    assert_parity(ref, out, 1e-9, True)
+    assert (ref["term"] == 4).sum() >= 64 * 2  # everybody times out, repeatedly
+
+
+def test_stepping_past_done_without_reset(S, O):
+    """Without auto-reset the reference object keeps integrating after done; the CUDA path does too
+    (the oracle's own IndexError at the end of the wind table is the reference's, wind.py:24)."""
+    cfg = S.load_config(base_settings__experiment=4, boat__fuel=40)
+    ref, out = rollout_both(S, O, cfg, 40, 120, "fp64", 0.05, False, 1)
+    assert_parity(ref, out, 1e-9, False)
+    assert (ref["term"] == 3).sum() == 40 * (120 - 40)  # out_of_fuel on every step after the 40th
+
+
+def test_unclipped_actions(S, O):
+    """boat_env.py:73 does not clip: |action| = 25 drives the rudder past pi/3 in one step."""
+    import torch
+    cfg = S.load_config(base_settings__experiment=3)
+    env = S.BatchedBoatEnv(cfg, 64, seed=1, precision="fp64", device=0, auto_reset=False)
+    env.reset()
+    a = torch.full((64,), 25.0, dtype=torch.float64, device="cuda")
+    a[::2] = -25.0
+    o = O.OracleEnv(O.params_from_config(cfg))
+    o.reset(0)
+    ro, rr, rd, rc = o.step(25.0)
+    obs, rew, done, info = env.step(a)
+    assert bool(done.all()) and bool((info["term"] == 5).all()) and rd and rc == 5
+    assert scaled_err(np_(obs)[1], ro).max() <= 1e-9 and abs(float(rew[1]) - rr) <= 1e-9 * abs(rr)
+    assert float(rew[1]) < -200.0  # the rudder penalty of boat_env.py:107-108 applies on the terminal step too
+    env.close()
+
+
+def test_argument_errors(S):
+    L = S.lib()
+    p = S.params_from_config(S.load_config())
+    h = C.c_void_p()
+    assert L.boatenv_create(C.byref(p), 0, 0, 0, 32, 0, C.byref(h)) == -1        # empty population
+    assert L.boatenv_create(C.byref(p), 4, 0, 0, 16, 0, C.byref(h)) == -1        # unknown precision
+    assert L.boatenv_create(C.byref(p), 4, 0, -1, 32, 0, C.byref(h)) == -1       # negative env id offset
+    assert L.boatenv_create(C.byref(p), 4, 0, 0, 32, 99, C.byref(h)) == -5       # no such device
+    assert L.boatenv_create(None, 4, 0, 0, 32, 0, C.byref(h)) == -1
+    assert L.boatenv_create(C.byref(p), 4, 0, 0, 32, 0, C.byref(h)) == 0
+    assert L.boatenv_step(h, None, None, None, None, None, None, 0, None) == -6  # step before reset
+    assert L.boatenv_reset(h, None, None, None) == 0
+    assert L.boatenv_step(h, None, None, None, None, None, None, 0, None) == -1  # null tensors
+    assert L.boatenv_get_field(h, 99, None, None) == -1
+    assert L.boatenv_wind_table(h, 4, None, None, None) == -1
+    assert L.boatenv_destroy(h) == 0 and L.boatenv_destroy(None) == -1
+    r = C.c_void_p()
+    assert L.boatreplay_create(0, 11, 1, 32, 0, C.byref(r)) == -1
+    assert L.boatreplay_create(8, 11, 1, 32, 0, C.byref(r)) == 0
+    assert L.boatreplay_sample(r, 4, 0, 0, 1, 1, 1, 1, 1, None, None) == -6      # empty buffer (np.random.choice(0, n))
+    assert L.boatreplay_destroy(r) == 0
+    t = C.c_void_p()
+    arr = (C.c_double * 4)(10, 10, 0.01, 0.1)
+    assert L.boattoy_create(7, 4, arr, 4, 0.0, 0, 32, 0, C.byref(t)) == -1       # unknown toy
+    assert L.boattoy_create(0, 4, arr, 3, 0.0, 0, 32, 0, C.byref(t)) == -1       # wrong parameter count
+    bad = S.BatchedBoatEnv(S.load_config(), 5, device=0)
+    bad.reset()
+    with pytest.raises(ValueError):
+        bad.step_k(np.zeros((3, 5), dtype=np.float32), 4)                        # [k, N] actions with the wrong k
+    bad.close()
