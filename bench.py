@@ -171,9 +171,14 @@ def cpu_baseline_leg(target_seconds: float = 12.0) -> dict:
     rate = steps / dt
     n_envs = int(max(16 * cores, min(rate * target_seconds / t_steps, 4_000_000 // t_steps * 16)))
     n_envs = (n_envs + 15) // 16 * 16
-    steps, dt = port.sample(n_envs, t_steps)
+    reps = max(1, min(4, int(round(target_seconds * rate / (n_envs * t_steps)))))  # memory-bounded chunks
+    steps = dt = 0.0
+    for _ in range(reps):
+        s_, d_ = port.sample(n_envs, t_steps)
+        steps += s_
+        dt += d_
     return {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_envs} envs x {t_steps} steps, experiment {EXPERIMENT}, uniform(-1,1) actions, "
+            "sample": f"{reps} x {n_envs} envs x {t_steps} steps, experiment {EXPERIMENT}, uniform(-1,1) actions, "
                       f"auto-reset, oracle/boat_oracle.c with {cores} pthreads ({dt:.1f} s)"}
 
 
