@@ -107,12 +107,11 @@ class BatchedBoatEnv:
         """BoatEnv.reset (boat_env.py:120-126) for all (or the masked) envs."""
         torch = _torch()
         m = None
-        if mask is not None:
+        if mask is not None:  # masked: only those envs (and their rows of self.obs) are rewritten
             m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
-        out = self.obs
-        if m is not None:  # masked: only those rows are rewritten
-            out = self.obs
-        _lib.check(self._L.boatenv_reset(self._h, None if m is None else m.data_ptr(), out.data_ptr(),
+            if m.numel() != self.n_envs:
+                raise ValueError("mask must have one entry per env")
+        _lib.check(self._L.boatenv_reset(self._h, None if m is None else m.data_ptr(), self.obs.data_ptr(),
                                          self._stream()), "boatenv_reset")
         return self.obs
 

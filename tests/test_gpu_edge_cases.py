@@ -166,3 +166,42 @@ def test_argument_errors(S):
     with pytest.raises(ValueError):
         bad.step_k(np.zeros((3, 5), dtype=np.float32), 4)                        # [k, N] actions with the wrong k
     bad.close()
+
+
+def test_masked_reset(S, O):
+    """reset(mask): BoatEnv.reset (boat_env.py:120-126) for the selected envs only -- new Boat, new Wind
+    (next episode's Philox draws), reset observation row; everybody else keeps stepping undisturbed."""
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    n = 300
+    a = S.BatchedBoatEnv(cfg, n, seed=9, precision="fp64", device=0, auto_reset=False)
+    b = S.BatchedBoatEnv(cfg, n, seed=9, precision="fp64", device=0, auto_reset=False)
+    a.reset(); b.reset()
+    for t in range(40):
+        acts = a.uniform_actions(t, 0.2)
+        a.step(acts); b.step(acts)
+    mask = torch.zeros(n, dtype=torch.bool, device="cuda")
+    mask[::7] = True
+    before = b.obs.clone()
+    obs = b.reset(mask)
+    assert torch.equal(obs[~mask], before[~mask])
+    assert torch.all(obs[mask][:, [0, 1, 2, 4, 5, 6, 7, 8]] == 0) and torch.all(obs[mask][:, 3] == 0.5)
+    assert torch.all(b.get_field("episode")[mask] == 1) and torch.all(b.get_field("episode")[~mask] == 0)
+    assert torch.all(b.get_field("index")[mask] == 0) and torch.all(b.get_field("index")[~mask] == 40)
+    with pytest.raises(ValueError):
+        b.reset(mask[:10])
+    p = O.params_from_config(cfg)
+    for t in range(40, 70):
+        acts = a.uniform_actions(t, 0.2)
+        oa, ra, _, _ = a.step(acts)
+        ob, rb, _, _ = b.step(acts)
+        assert torch.equal(oa[~mask], ob[~mask]) and torch.equal(ra[~mask], rb[~mask])
+    # a re-started env follows the oracle fed with episode 1's draws
+    i = 7
+    s_y, knots = b.episode_draws(i, 1)
+    o = O.OracleEnv(p)
+    o.reset(s_y, knots[0], knots[1])
+    for t in range(40, 70):
+        ro, rr, rd, rc = o.step(float(a.uniform_actions(t, 0.2)[i]))
+    assert scaled_err(np_(b.obs)[i], ro).max() <= 1e-9
+    a.close(); b.close()
