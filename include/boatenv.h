@@ -128,6 +128,10 @@ BOATENV_API int boatenv_step_k(boatenv_t h, const void *actions, int64_t action_
  * call a CPU-side agent loop (main.py:80-81) makes. */
 BOATENV_API int boatenv_step_host(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host,
                       uint8_t *done_host, uint32_t flags);
+/* The same, also returning the termination codes (BOATENV_TERM_*) of this step in term_host: what the
+ * single-env drop-in needs to maintain info['termination'] and its counters (boat_env.py:87-105). */
+BOATENV_API int boatenv_step_host_term(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host,
+                           uint8_t *done_host, uint8_t *term_host, uint32_t flags);
 
 /* ---- state access (env.boat.* of main.py:94, recorder.py:36,46) -------------------- */
 

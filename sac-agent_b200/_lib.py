@@ -39,6 +39,7 @@ SIGNATURES = {
     "boatenv_step": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, u32, vp]),
     "boatenv_step_k": (C.c_int, [vp, vp, i64, i32, vp, vp, vp, vp, vp, u32, vp]),
     "boatenv_step_host": (C.c_int, [vp, vp, vp, vp, vp, u32]),
+    "boatenv_step_host_term": (C.c_int, [vp, vp, vp, vp, vp, vp, u32]),
     "boatenv_get_field": (C.c_int, [vp, C.c_int, vp, vp]),
     "boatenv_set_field": (C.c_int, [vp, C.c_int, vp, vp]),
     "boatenv_wind_table": (C.c_int, [vp, i64, vp, vp, vp]),

@@ -319,6 +319,13 @@ class BoatEnv:
         self.action_space = self._b.action_space
         self.observation_space = self._b.observation_space
         self.low_state, self.high_state = self.observation_space.low, self.observation_space.high
+        torch = _torch()
+        # pinned host buffers of the one-call-per-step host path (boatenv_step_host_term)
+        self._h_act = torch.zeros(1, dtype=self._b.dtype).pin_memory()
+        self._h_obs = torch.zeros((1, 11), dtype=self._b.dtype).pin_memory()
+        self._h_rew = torch.zeros(1, dtype=self._b.dtype).pin_memory()
+        self._h_done = torch.zeros(1, dtype=torch.uint8).pin_memory()
+        self._h_term = torch.zeros(1, dtype=torch.uint8).pin_memory()
         self._b.reset()  # BoatEnv.__init__ builds a Boat (boat_env.py:15)
 
     def reset(self):
@@ -328,18 +335,20 @@ class BoatEnv:
         return self.state
 
     def step(self, action):
-        torch = _torch()
         self.action = action
-        a = torch.tensor([float(np.asarray(action).reshape(-1)[0])], dtype=self._b.dtype, device=self._b.device)
-        obs, reward, done, extra = self._b.step(a)
-        code = int(extra["term"][0].item())
-        self.reward = float(reward[0].item())
+        self._h_act[0] = float(np.asarray(action).reshape(-1)[0])
+        b = self._b
+        _lib.check(b._L.boatenv_step_host_term(b._h, self._h_act.data_ptr(), self._h_obs.data_ptr(),
+                                               self._h_rew.data_ptr(), self._h_done.data_ptr(),
+                                               self._h_term.data_ptr(), 0), "boatenv_step_host_term")
+        code = int(self._h_term[0])
+        self.reward = float(self._h_rew[0])
         if code:
             self.info["termination"] = TERM_NAMES[code]
             self.info[TERM_NAMES[code]] += 1
         self.info["episode_reward"] += self.reward
-        self.state = obs[0].double().cpu().numpy()
-        return self.state, self.reward, bool(done[0].item()), self.info
+        self.state = self._h_obs[0].double().numpy().copy()  # a fresh array every call, like boat_env.py:309
+        return self.state, self.reward, bool(self._h_done[0]), self.info
 
     def render(self):
         pass

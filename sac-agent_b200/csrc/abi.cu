@@ -36,7 +36,7 @@ struct boatenv_handle {
     double *counters_out_dev;  // 8 doubles
     // step_host staging
     void *h_act, *h_obs, *h_rew;
-    uint8_t *h_done;
+    uint8_t *h_done, *h_term;
     cudaStream_t copy_in, compute, copy_out;
     cudaEvent_t ev_in[8], ev_k[8];
     bool host_path_ready;
@@ -310,6 +310,7 @@ int boatenv_destroy(boatenv_t h) {
     cudaFree(h->h_obs);
     cudaFree(h->h_rew);
     cudaFree(h->h_done);
+    cudaFree(h->h_term);
     if (h->host_path_ready) {
         cudaStreamDestroy(h->copy_in);
         cudaStreamDestroy(h->compute);
@@ -388,6 +389,7 @@ static int ensure_host_path(boatenv_t h) {
     CUDA_TRY(cudaMalloc(&h->h_obs, n * kObsDim * h->esize));
     CUDA_TRY(cudaMalloc(&h->h_rew, n * h->esize));
     CUDA_TRY(cudaMalloc((void **)&h->h_done, n));
+    CUDA_TRY(cudaMalloc((void **)&h->h_term, n));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
@@ -399,8 +401,22 @@ static int ensure_host_path(boatenv_t h) {
     return BOATENV_OK;
 }
 
+static int step_host_impl(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host, uint8_t *done_host,
+                          uint8_t *term_host, uint32_t flags);
+
 int boatenv_step_host(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host, uint8_t *done_host,
                       uint32_t flags) {
+    return step_host_impl(h, actions_host, obs_host, reward_host, done_host, nullptr, flags);
+}
+
+int boatenv_step_host_term(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host,
+                           uint8_t *done_host, uint8_t *term_host, uint32_t flags) {
+    if (!term_host) return BOATENV_EINVAL;
+    return step_host_impl(h, actions_host, obs_host, reward_host, done_host, term_host, flags);
+}
+
+static int step_host_impl(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host, uint8_t *done_host,
+                          uint8_t *term_host, uint32_t flags) {
     if (!h || !actions_host || !obs_host || !reward_host || !done_host) return BOATENV_EINVAL;
     if (!h->was_reset) return BOATENV_ESTATE;
     CUDA_TRY(cudaSetDevice(h->device));
@@ -432,6 +448,7 @@ int boatenv_step_host(boatenv_t h, const void *actions_host, void *obs_host, voi
         a.obs_out = h->h_obs;
         a.reward_out = h->h_rew;
         a.done_out = h->h_done;
+        a.term_out = term_host ? h->h_term : nullptr;
         a.flags = flags;
         a.reverse = rev;
         CUDA_TRY(h->precision == 32 ? launch_step_f32(h->cfg, a, h->compute) : launch_step_f64(h->cfg, a, h->compute));
@@ -442,6 +459,7 @@ int boatenv_step_host(boatenv_t h, const void *actions_host, void *obs_host, voi
         CUDA_TRY(cudaMemcpyAsync((char *)reward_host + b * es, (char *)h->h_rew + b * es, cnt * es,
                                  cudaMemcpyDeviceToHost, h->copy_out));
         CUDA_TRY(cudaMemcpyAsync(done_host + b, h->h_done + b, cnt, cudaMemcpyDeviceToHost, h->copy_out));
+        if (term_host) CUDA_TRY(cudaMemcpyAsync(term_host + b, h->h_term + b, cnt, cudaMemcpyDeviceToHost, h->copy_out));
     }
     CUDA_TRY(cudaStreamSynchronize(h->copy_out));
     return BOATENV_OK;

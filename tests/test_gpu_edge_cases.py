@@ -205,3 +205,21 @@ def test_masked_reset(S, O):
         ro, rr, rd, rc = o.step(float(a.uniform_actions(t, 0.2)[i]))
     assert scaled_err(np_(b.obs)[i], ro).max() <= 1e-9
     a.close(); b.close()
+
+
+def test_single_env_step_latency(S):
+    """The single-env drop-in makes ONE blocking C-ABI call per step (pinned host buffers): it must not be
+    slower than the reference's own CPU step (0.10-0.35 ms) it replaces."""
+    import time
+    env = S.BoatEnv(S.load_config(base_settings__experiment=6), seed=1, precision="fp64", device=0)
+    env.reset()
+    a = np.array([0.01], dtype=np.float32)
+    for _ in range(50):
+        env.step(a)
+    t0 = time.perf_counter()
+    for _ in range(300):
+        env.step(a)
+    per_step = (time.perf_counter() - t0) / 300
+    print(f"single-env BoatEnv.step: {per_step * 1e6:.0f} us")
+    assert per_step < 0.5e-3
+    env.close()
