@@ -1,8 +1,12 @@
-// boat_step.cuh -- the batched BoatEnv.step kernel (boat_env.py:67-115), one thread per
-// env, K fused sub-steps with the env state held in registers, in-kernel termination
-// cascade, statistics and auto-reset.  Instantiated for float (production) in
-// step_f32.cu and for double (validation, reference operation order, compiled with
-// -fmad=false) in step_f64.cu.
+// boat_step.cuh -- the batched BoatEnv.step kernel (boat_env.py:67-115): one thread per env, state in
+// registers across K fused sub-steps, in-kernel termination cascade, statistics and auto-reset.
+//   * persistent, self-contained step warps walk the 32-env state blocks of the tile-blocked layout
+//     (common.cuh); each keeps one TMA bulk copy (cp.async.bulk + mbarrier) of its next block in flight;
+//   * state goes back with 128-bit stores, the [32][11] observation tile with one bulk store;
+//   * K = 1 kernels of the random-wind experiments are warp-specialised: wind-setup requests travel
+//     through a shared-memory ring to dedicated setup warps (wind_setup.cuh does the maths).
+// Instantiated for float (production) in step_f32.cu and for double (validation, reference operation
+// order, compiled with -fmad=false) in step_f64.cu.  Design notes and measurements: DESIGN.md section 4.
 #pragma once
 #include "common.cuh"
 #include "wind_setup.cuh"
