@@ -333,9 +333,7 @@ int boatenv_reset(boatenv_t h, const uint8_t *mask, void *obs_out, void *stream)
 
 static int step_common(boatenv_t h, StepArgs &a, cudaStream_t st) {
     if (!h->was_reset) return BOATENV_ESTATE;
-#ifndef BOAT_NO_REVERSE
     a.reverse = (int)(h->launch_parity++ & 1u);
-#endif
     if (!a.actions || !a.obs_out || !a.reward_out || !a.done_out || a.ksteps < 1) return BOATENV_EINVAL;
     if (!aligned16(a.obs_out)) return BOATENV_EALIGN;
     CUDA_TRY(cudaSetDevice(h->device));

@@ -213,11 +213,7 @@ __device__ __forceinline__ void load_vecs(const char *sec, int lane, T (&out)[NS
 
 // State stores: default (evict-normal) L2 policy, unlike the streamed outputs: the state is the only
 // data the NEXT launch reads again, and launches alternate their sweep direction (boat_step.cuh).
-#ifdef BOAT_STATE_STCS
-template <typename V> __device__ __forceinline__ void st_state(V *p, const V &v) { __stcs(p, v); }
-#else
 template <typename V> __device__ __forceinline__ void st_state(V *p, const V &v) { *p = v; }
-#endif
 
 // 128-bit stores of NS scalars of lane `lane` into a section.
 template <typename T, int NS>
