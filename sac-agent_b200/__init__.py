@@ -12,7 +12,7 @@ from ._lib import BoatEnvError, lib, library_path  # noqa: F401
 from .boat_env import BatchedBoatEnv, BoatEnv, Box, TERM_NAMES  # noqa: F401
 from .buffer import ReplayBuffer  # noqa: F401
 from .toy_envs import ToyCar, ToyParachute  # noqa: F401
-from .recorder import BatchedRecorder  # noqa: F401
+from .csv_export import BatchedRecorder  # noqa: F401
 from .sharding import all_reduce_counters, make_sharded_env, shard_range  # noqa: F401
 
 __all__ = ["AttrDict", "load_config", "params_from_config", "BoatEnvError", "lib", "library_path",

@@ -76,12 +76,20 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
             const double *brow = c.basis + (size_t)rem * fp;
             const double *u = kn + curve * kMaxKnots;
             double acc0 = 0.0, acc1 = 0.0;
-            int k = 0;
-            for (; k + 1 < fp; k += 2) {
-                acc0 = fma(__ldg(brow + k), u[k], acc0);
-                acc1 = fma(__ldg(brow + k + 1), u[k + 1], acc1);
+            if (fp == 8) {  // the reference's default (original_config.yaml:63): fully unrolled
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                    acc0 = fma(__ldg(brow + k), u[k], acc0);
+                    acc1 = fma(__ldg(brow + k + 1), u[k + 1], acc1);
+                }
+            } else {
+                int k = 0;
+                for (; k + 1 < fp; k += 2) {
+                    acc0 = fma(__ldg(brow + k), u[k], acc0);
+                    acc1 = fma(__ldg(brow + k + 1), u[k + 1], acc1);
+                }
+                if (k < fp) acc0 = fma(__ldg(brow + k), u[k], acc0);
             }
-            if (k < fp) acc0 = fma(__ldg(brow + k), u[k], acc0);
             coef[t] = acc0 + acc1;
         }
     }
@@ -95,14 +103,25 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
     double mn = inf, mx = -inf;
     if (cv < nc && sub < np) {
         const double *cf = coef + (cv * np + sub) * 4;
+        const double k0 = cf[0], k1 = cf[1], k2 = cf[2], k3 = cf[3];
+        const int r_base = sub * c.Lm1;
         auto consider = [&](int index) {
-            const double v = eval_sample(c, coef, cv, index);
-            mn = fmin(mn, v);
-            mx = fmax(mx, v);
+            // samples inside this lane's own piece (the usual case) are evaluated from registers, exactly as
+            // eval_sample would (same piece, same s); neighbours in other pieces take the table path
+            const int r = index * np - r_base;
+            double v;
+            if (index >= 0 && index < c.L && r >= 0 && r < c.Lm1) {
+                const double sl = (double)r * c.inv_Lm1;
+                v = fma(fma(fma(k3, sl, k2), sl, k1), sl, k0);
+            } else {
+                v = eval_sample(c, coef, cv, index);
+            }
+            mn = (v < mn) ? v : mn;  // no NaNs here: plain compares instead of fmin / fmax
+            mx = (v > mx) ? v : mx;
         };
         consider(__ldg(c.piece_bounds + 2 * sub));      // first sample that falls into this piece
         consider(__ldg(c.piece_bounds + 2 * sub + 1));  // last one
-        const float A = 3.0f * (float)cf[3], B = 2.0f * (float)cf[2], C0 = (float)cf[1];
+        const float A = 3.0f * (float)k3, B = 2.0f * (float)k2, C0 = (float)k1;
         const float nanf_ = __int_as_float(0x7fc00000);
         float s1 = nanf_, s2 = nanf_;
         if (fabsf(A) > 1e-6f * (fabsf(B) + fabsf(C0))) {
@@ -131,8 +150,9 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
     // segmented reduction: each half-warp reduces its own curve
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {
-        mn = fmin(mn, __shfl_xor_sync(FULL, mn, o));
-        mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+        const double on = __shfl_xor_sync(FULL, mn, o), ox = __shfl_xor_sync(FULL, mx, o);
+        mn = (on < mn) ? on : mn;
+        mx = (ox > mx) ? ox : mx;
     }
     // lanes 0..15 hold curve A's extremes, 16..31 curve B's; lanes 0..7 do the fold
     const double mnB = __shfl_sync(FULL, mn, 16), mxB = __shfl_sync(FULL, mx, 16);
