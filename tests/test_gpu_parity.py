@@ -412,7 +412,7 @@ def test_full_size_properties(S):
     not need the oracle -- determinism, counter consistency, fuel bookkeeping."""
     import torch
     cfg = S.load_config(base_settings__experiment=6)
-    n, T = 4 * 1024 * 1024, 40
+    n, T = 16 * 1024 * 1024, 40   # the full per-GPU population of the benchmark
     runs = []
     for _ in range(2):
         env = make_env(S, cfg, n, "fp32", seed=1, auto_reset=True)
