@@ -118,7 +118,8 @@ class BatchedBoatEnv:
     def step(self, actions):
         """BoatEnv.step (boat_env.py:67-115) for every env.  Returns (obs, reward, done, info);
         info holds the per-env termination codes and, under auto-reset, the terminal
-        observations of the envs that finished."""
+        observations of the envs that finished.  The returned tensors are the env's own output
+        buffers (no allocation per step): the next step overwrites them, clone what must survive."""
         a = self._actions(actions)
         flags = AUTO_RESET if self.auto_reset else 0
         _lib.check(self._L.boatenv_step(self._h, a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
