@@ -82,6 +82,11 @@ def boat_case(name, experiment, precision, n, scale, bytes_per_step, warm, iters
 def main():
     torch.cuda.set_device(0)
     M = 1 << 20
+    if os.environ.get("BENCH_EXTRA_ONLY") == "k8":
+        boat_case("exp6_fp32_16M_k8", 6, "fp32", 16 * M, 1.0, 4 + 5 + (112 + 44) / 8, 100, 30, k=8)
+        boat_case("exp6_fp32_16M_k8_long_episodes", 6, "fp32", 16 * M, 0.02, 4 + 5 + (112 + 44) / 8, 30, 30, k=8)
+        boat_case("exp6_fp32_16M_k1_long_episodes", 6, "fp32", 16 * M, 0.02, 165, 100, 100)
+        return
     # BASELINE.json configs[1]: exp 3, 4096 envs, fp64 (launch-latency bound at this size) and the same at 4M envs
     boat_case("exp3_fp64_4096", 3, "fp64", 4096, 0.05, 249, 50, 200)
     boat_case("exp3_fp64_4M", 3, "fp64", 4 * M, 0.05, 249, 50, 50)
@@ -92,6 +97,9 @@ def main():
     boat_case("exp6_fp32_16M", 6, "fp32", 16 * M, 1.0, 165, 600, 100)
     # K fused sub-steps (obs only at the end): bytes per env-step shrink, the kernel turns compute bound
     boat_case("exp6_fp32_16M_k8", 6, "fp32", 16 * M, 1.0, 4 + 5 + (112 + 44) / 8, 100, 30, k=8)
+    # the same with long episodes (small steering noise: nobody resets within the run)
+    boat_case("exp6_fp32_16M_k8_long_episodes", 6, "fp32", 16 * M, 0.02, 4 + 5 + (112 + 44) / 8, 30, 30, k=8)
+    boat_case("exp6_fp32_16M_k1_long_episodes", 6, "fp32", 16 * M, 0.02, 165, 100, 100)
 
     # replay buffer: batched store, sample-gather (agent/buffer.py), fused step+store
     n, cap = 4 * M, 16 * M
