@@ -43,19 +43,29 @@ def emit(name, ms, units, unit_name, bytes_per_unit=None, **extra):
     print(json.dumps(line), flush=True)
 
 
-def boat_case(name, experiment, precision, n, scale, bytes_per_step, warm, iters, k=1):
+def boat_case(name, experiment, precision, n, scale, bytes_per_step, warm, iters, k=1, per_substep=False):
     cfg = S.load_config(base_settings__experiment=experiment)
     env = S.BatchedBoatEnv(cfg, n, seed=1, precision=precision, device=0, auto_reset=True)
     env.reset()
     acts = env.uniform_actions(0, scale)
+    acts_k = torch.empty((k, n), dtype=acts.dtype, device=acts.device) if per_substep else None
     t = [0]
 
-    def step():
-        env.uniform_actions(t[0], scale, out=acts)
+    def fill():
+        if per_substep:   # the policy emits a fresh action for every sub-step: same episode statistics as K = 1
+            for q in range(k):
+                env.uniform_actions(t[0] * k + q, scale, out=acts_k[q])
+        else:             # action repeat (frame skip): one action held for the k sub-steps
+            env.uniform_actions(t[0], scale, out=acts)
+
+    def launch():
         if k == 1:
             env.step(acts)
         else:
-            env.step_k(acts, k)
+            env.step_k(acts_k if per_substep else acts, k)
+
+    def step():
+        fill(); launch()
         t[0] += 1
     for _ in range(warm):
         step()
@@ -64,12 +74,9 @@ def boat_case(name, experiment, precision, n, scale, bytes_per_step, warm, iters
     # ~20 steps); only the step launch sits between the event pairs, like in bench.py
     pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
     for a, b in pairs:
-        env.uniform_actions(t[0], scale, out=acts)
+        fill()
         a.record()
-        if k == 1:
-            env.step(acts)
-        else:
-            env.step_k(acts, k)
+        launch()
         b.record()
         t[0] += 1
     torch.cuda.synchronize()
@@ -84,6 +91,8 @@ def main():
     M = 1 << 20
     if os.environ.get("BENCH_EXTRA_ONLY") == "k8":
         boat_case("exp6_fp32_16M_k8", 6, "fp32", 16 * M, 1.0, 4 + 5 + (112 + 44) / 8, 100, 30, k=8)
+        boat_case("exp6_fp32_16M_k8_per_substep_actions", 6, "fp32", 16 * M, 1.0, 4 + 4 + 5 + (112 + 44) / 8, 80, 30, k=8,
+                  per_substep=True)
         boat_case("exp6_fp32_16M_k8_long_episodes", 6, "fp32", 16 * M, 0.02, 4 + 5 + (112 + 44) / 8, 30, 30, k=8)
         boat_case("exp6_fp32_16M_k1_long_episodes", 6, "fp32", 16 * M, 0.02, 165, 100, 100)
         return
@@ -97,6 +106,8 @@ def main():
     boat_case("exp6_fp32_16M", 6, "fp32", 16 * M, 1.0, 165, 600, 100)
     # K fused sub-steps (obs only at the end): bytes per env-step shrink, the kernel turns compute bound
     boat_case("exp6_fp32_16M_k8", 6, "fp32", 16 * M, 1.0, 4 + 5 + (112 + 44) / 8, 100, 30, k=8)
+    boat_case("exp6_fp32_16M_k8_per_substep_actions", 6, "fp32", 16 * M, 1.0, 4 + 4 + 5 + (112 + 44) / 8, 80, 30, k=8,
+              per_substep=True)
     # the same with long episodes (small steering noise: nobody resets within the run)
     boat_case("exp6_fp32_16M_k8_long_episodes", 6, "fp32", 16 * M, 0.02, 4 + 5 + (112 + 44) / 8, 30, 30, k=8)
     boat_case("exp6_fp32_16M_k1_long_episodes", 6, "fp32", 16 * M, 0.02, 165, 100, 100)

@@ -29,6 +29,9 @@ struct boatenv_handle {
     size_t esize;
     bool was_reset;
     unsigned launch_parity;    // consecutive step launches sweep the state in opposite directions
+    uint2 *kq_entries;         // episode-end queue of the K > 1 kernels (allocated on first use)
+    unsigned *kq_counts;
+    long long kq_total;
     double *basis_dev;
     int *piece_bounds_dev;
     int32_t *ovr_s_y;
@@ -304,6 +307,8 @@ int boatenv_destroy(boatenv_t h) {
     cudaFree(h->counters_out_dev);
     cudaFree(h->basis_dev);
     cudaFree(h->piece_bounds_dev);
+    cudaFree(h->kq_entries);
+    cudaFree(h->kq_counts);
     cudaFree(h->ovr_s_y);
     cudaFree(h->ovr_knots);
     cudaFree(h->h_act);
@@ -377,6 +382,17 @@ int boatenv_step_k(boatenv_t h, const void *actions, int64_t action_stride, int3
     a.term_out = term_out;
     a.steps_out = steps_out;
     a.flags = flags;
+    if (k > 1 && h->cfg.ncurves > 0 && (flags & BOATENV_AUTO_RESET)) {  // episode-end queue of the fused kernels
+        if (!h->kq_entries) {
+            CUDA_TRY(cudaSetDevice(h->device));
+            h->kq_total = num_blocks(h->cfg.n_envs) * 32 + 1024LL * kWarpsPerCta * 32;
+            CUDA_TRY(cudaMalloc((void **)&h->kq_entries, (size_t)h->kq_total * sizeof(uint2)));
+            CUDA_TRY(cudaMalloc((void **)&h->kq_counts, 4096 * sizeof(unsigned)));
+        }
+        a.kq_entries = h->kq_entries;
+        a.kq_counts = h->kq_counts;
+        a.kq_total = h->kq_total;
+    }
     return step_common(h, a, (cudaStream_t)stream);
 }
 

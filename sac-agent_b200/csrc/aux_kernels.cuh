@@ -50,6 +50,34 @@ __global__ void __launch_bounds__(kTile) boat_reset_kernel(const __grid_constant
     }
 }
 
+// Follow-up of a K > 1 step launch: the episode-end queue (one region per step CTA) is drained at full
+// occupancy -- one warp-cooperative wind setup per entry, the new episode's first-piece coefficients go
+// straight into the env's state block.  Warps are dealt to regions round-robin.
+template <typename T>
+__global__ void __launch_bounds__(kTile, 3) boat_setup_queue_kernel(const __grid_constant__ DevCfg c,
+                                                                   const uint2 *__restrict__ entries,
+                                                                   const unsigned *__restrict__ counts, int n_regions,
+                                                                   int cap, int warps_per_region) {
+    __shared__ double scratch_s[kWarpsPerCta][kScratchDoubles];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = (int)blockIdx.x * kWarpsPerCta + warp;
+    const int region = w % n_regions, j0 = w / n_regions;
+    if (j0 >= warps_per_region) return;
+    const unsigned cnt = counts[region];
+    double *scr = scratch_s[warp];
+    for (unsigned e = (unsigned)j0; e < cnt; e += (unsigned)warps_per_region) {
+        const uint2 en = __ldg(entries + (size_t)region * cap + e);  // warp-uniform
+        wind_setup_warp(c, (long long)en.x, en.y, 0, scr);
+        if (lane < c.ncurves) {  // lane 0: first curve, lane 1: second curve
+            T w4[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) w4[m] = (T)scr[lane * 4 + m];
+            store_vecs<T, 4>(block_section(c, en.x, lane ? c.off_wb : c.off_wa), (int)(en.x & 31u), w4);
+        }
+        __syncwarp();
+    }
+}
+
 // env.boat.wind.wind_velocity / wind_angle (wind.py:16-17) of one env's CURRENT episode,
 // as the step kernel sees them: per-piece folded coefficients evaluated at every sample.
 // One warp.

@@ -368,13 +368,14 @@ struct WarpSmem {
 template <typename T>
 struct CtaSmem {
     WarpSmem<T> warp;
-    int queue_off, setup_scratch_off, setup_scratch_bytes, bytes;
+    int queue_off, setup_scratch_off, setup_scratch_bytes, kq_off, bytes;
     __host__ __device__ CtaSmem(int block_bytes, int ncurves, int npieces, int n_setup)
         : warp(block_bytes, n_setup > 0 ? 0 : scratch_doubles(ncurves, npieces)) {
         queue_off = kWarpsPerCta * warp.bytes;
         setup_scratch_off = queue_off + (n_setup > 0 ? (int)sizeof(SetupQueue) : 0);
         setup_scratch_bytes = (scratch_doubles(ncurves, npieces) * 8 + 127) / 128 * 128;
-        bytes = setup_scratch_off + n_setup * setup_scratch_bytes;
+        kq_off = setup_scratch_off + n_setup * setup_scratch_bytes;  // two counters of the K > 1 episode-end queue
+        bytes = kq_off + 16;
     }
 };
 
@@ -434,6 +435,21 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             return;
         }
     }
+    // K > 1 kernels of the random-wind experiments: finished episodes are deferred to a follow-up kernel
+    const bool kq_on = KMULTI && kCurves && a.kq_entries != nullptr;
+    unsigned *kq_cnt = reinterpret_cast<unsigned *>(smem_raw + cta.kq_off);  // [0] entries pushed, [1] warps finished
+    if (KMULTI && kCurves) {
+        if (threadIdx.x == 0) { kq_cnt[0] = 0u; kq_cnt[1] = 0u; }
+        __syncthreads();
+    }
+    auto kq_finish = [&]() {  // the last step warp of the CTA publishes the region's entry count
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            if (atomicAdd(kq_cnt + 1, 1u) == (unsigned)(kWarpsPerCta - 1))
+                a.kq_counts[blockIdx.x] = *reinterpret_cast<volatile unsigned *>(kq_cnt);
+        }
+    };
     unsigned char *wbase = smem_raw + (size_t)warp * lay.bytes;
     unsigned char *stage_base = wbase;                                  // kStages * bb   (16-byte aligned)
     T *tile = reinterpret_cast<T *>(wbase + lay.tile_off);              // [32][11]
@@ -452,6 +468,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
     int seq = blk_first + (int)blockIdx.x * kWarpsPerCta + warp;  // CTA-major: 8 consecutive blocks per CTA (warp-major measured 2 % slower)
     if (seq >= blk_end) {
         if (kSetup > 0 && lane == 0) atomicAdd(&queue->producers_done, 1u);
+        if (kq_on) kq_finish();
         return;
     }
     auto block_of = [&](int q) { return rev ? (blk_last - (q - blk_first)) : q; };
@@ -683,7 +700,23 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                         }
                     }
                 }
-                unsigned todo = kSetup > 0 ? 0u : __ballot_sync(FULL, need_setup && active && (!is_done || auto_reset));
+                bool deferred = false;
+                if (kq_on && is_done && auto_reset) {
+                    // K > 1: the env is frozen for the rest of the window, so its new wind coefficients are not
+                    // needed before the next launch: queue (env, new episode) for boat_setup_queue_kernel and do
+                    // only the cheap part of Boat.__init__ (boat_env.py:144-201) here
+                    const unsigned pos = atomicAdd(kq_cnt, 1u);
+                    a.kq_entries[(size_t)blockIdx.x * a.kq_cap + pos] = make_uint2((unsigned)i, episode + 1u);
+#pragma unroll
+                    for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
+                    index = 0;
+                    episode += 1u;
+                    wind_dirty = false;  // the old episode's coefficients are dead; the follow-up kernel writes the new ones
+                    stage_reset_obs<T>(c, row, (T)0);  // only experiment 2 starts off the centre line (:166-167)
+                    deferred = true;
+                }
+                unsigned todo = kSetup > 0 ? 0u
+                                           : __ballot_sync(FULL, need_setup && active && !deferred && (!is_done || auto_reset));
                 while (todo) {
                     const int src = __ffs(todo) - 1;
                     todo &= todo - 1;
@@ -749,6 +782,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             atomicAdd(&queue->producers_done, 1u);
         }
     }
+    if (kq_on) kq_finish();
     if (tile_in_flight && lane == 0) tma_store_wait_all();  // smem must stay valid until the last store has read it
 }
 

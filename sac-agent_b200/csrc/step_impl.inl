@@ -1,5 +1,7 @@
 // step_impl.inl -- included by step_f32.cu (REAL=float) and step_f64.cu (REAL=double):
 // instantiates the kernels for one precision and defines its launchers.
+#include <algorithm>
+
 #include "aux_kernels.cuh"
 #include "launch.h"
 
@@ -14,7 +16,8 @@ static inline unsigned grid_for(long long n, int block) { return (unsigned)((n +
 // Persistent launch: enough CTAs to fill every SM at the kernel's occupancy (queried once per
 // instantiation and shared-memory size), never more than there are 8-warp groups of blocks.
 template <int WK, bool KMULTI>
-static cudaError_t launch_step_wk(const DevCfg &c, const StepArgs &a, cudaStream_t st) {
+static cudaError_t launch_step_wk(const DevCfg &c, const StepArgs &a_in, cudaStream_t st) {
+    StepArgs a = a_in;
     auto kern = boat_step_kernel<REAL, WK, KMULTI>;
     constexpr int n_setup = setup_warps<WK, KMULTI>();
     constexpr int threads = kTile + 32 * n_setup;
@@ -37,7 +40,26 @@ static cudaError_t launch_step_wk(const DevCfg &c, const StepArgs &a, cudaStream
     long long grid = (nblk + kWarpsPerCta - 1) / kWarpsPerCta;
     const long long resident = (long long)n_sm * ctas_per_sm;
     if (grid > resident) grid = resident;
+    constexpr bool kCurves = (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH);
+    bool deferred = false;
+    if (KMULTI && kCurves && a.kq_entries && (a.flags & BOATENV_AUTO_RESET)) {
+        // one queue region per CTA, big enough for every env the CTA can touch in this launch
+        const long long tiles_per_warp = (nblk + grid * kWarpsPerCta - 1) / (grid * kWarpsPerCta);
+        const long long cap = tiles_per_warp * kWarpsPerCta * 32;
+        if (grid * cap <= a.kq_total && cap < (1LL << 31)) {
+            a.kq_cap = (int)cap;
+            deferred = true;
+        }
+    }
+    if (!deferred) a.kq_entries = nullptr;
     kern<<<(unsigned)grid, threads, smem, st>>>(c, a);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess || !deferred) return err;
+    const int warps_per_region = (int)std::max(1LL, (long long)n_sm * 64 / grid);  // ~2 waves of resident warps
+    const long long setup_warps_total = grid * warps_per_region;
+    boat_setup_queue_kernel<REAL><<<(unsigned)((setup_warps_total + kWarpsPerCta - 1) / kWarpsPerCta), kTile, 0, st>>>(
+        c, a.kq_entries, a.kq_counts, (int)grid, a.kq_cap, warps_per_region);
+    count_launch();
     return cudaGetLastError();
 }
 

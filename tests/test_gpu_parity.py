@@ -282,6 +282,54 @@ def test_step_k_equals_k_single_steps(S):
         a.close(); b.close()
 
 
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("per_substep_actions", [False, True])
+def test_step_k_auto_reset_matches_oracle(S, O, precision, per_substep_actions):
+    """K fused sub-steps with auto-reset against an env-by-env emulation on the oracle: an env stops at its
+    first done inside the window (reward = sum over executed sub-steps, steps = their number), the next
+    window starts its next episode -- whose wind coefficients come from the deferred episode-end queue."""
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    n, K, W, E = 192, 5, 90, 80
+    env = make_env(S, cfg, n, precision, seed=31, auto_reset=True)
+    s_y, knots = host_draws(env, E)
+    env.reset()
+    p = O.params_from_config(cfg)
+    oracles = [O.OracleEnv(p) for _ in range(n)]
+    episode = [0] * n
+    for i, o in enumerate(oracles):
+        o.reset(int(s_y[0, i]), knots[0, i, 0], knots[0, i, 1])
+    tol = TOL64 if precision == "fp64" else TOL32
+    n_done = 0
+    for w in range(W):
+        if per_substep_actions:
+            acts = torch.stack([env.uniform_actions(w * K + k, 1.5).clone() for k in range(K)])
+        else:
+            acts = env.uniform_actions(w, 1.5).clone()
+        obs, rew, done, info = env.step_k(acts, K)
+        a_np, obs_np, rew_np = np_(acts), np_(obs), np_(rew)
+        done_np, term_np, steps_np = np_(done), np_(info["term"]), np_(info["steps"])
+        for i, o in enumerate(oracles):
+            r_sum, d, code, steps, last = 0.0, False, 0, 0, None
+            for k in range(K):
+                a = a_np[k, i] if per_substep_actions else a_np[i]
+                last, r, d, code = o.step(float(a))
+                r_sum += r
+                steps += 1
+                if d:
+                    break
+            assert bool(done_np[i]) == d and int(term_np[i]) == code and int(steps_np[i]) == steps
+            assert abs(rew_np[i] - r_sum) <= tol * max(1.0, abs(r_sum))
+            if d:
+                n_done += 1
+                episode[i] += 1
+                last = o.reset(int(s_y[episode[i], i]), knots[episode[i], i, 0], knots[episode[i], i, 1])
+            assert scaled_err(obs_np[i], last).max() <= tol
+    assert n_done > n  # plenty of episode ends went through the queue
+    assert env.counters()["episodes"] == n_done
+    env.close()
+
+
 def test_shard_invariance(S):
     """Philox is keyed by the GLOBAL env id: a 1024-env population equals two 512-env
     shards (what ranks 0 and 1 of a 2-GPU run hold), bit for bit."""
