@@ -279,16 +279,19 @@ int boatenv_create(const boatenv_params *params, int64_t n_envs, uint64_t seed, 
     if (e == cudaSuccess) e = cudaMemset(cfg.state, 0xFF, state_bytes);  // episode -1: reset() makes it 0
     if (e == cudaSuccess) e = cudaMemset(cfg.counters, 0, kCounterSlots * 32 * sizeof(double));
     cfg.basis = h->basis_dev;
-    {   // first / last sample of every spline piece: ceil(j*Lm1/np), floor((j+1)*Lm1/np)
+    {   // first / last sample that piece_of() assigns to piece j: floor(index*np / Lm1) == j, i.e.
+        // ceil(j*Lm1/np) <= index <= floor(((j+1)*Lm1 - 1)/np); the last piece also owns sample L-1
         std::vector<int> pb(2 * (size_t)cfg.npieces);
         for (int j = 0; j < cfg.npieces; ++j) {
             pb[2 * j] = (int)(((long long)j * cfg.Lm1 + cfg.npieces - 1) / cfg.npieces);
-            pb[2 * j + 1] = (int)(((long long)(j + 1) * cfg.Lm1) / cfg.npieces);
+            pb[2 * j + 1] = j == cfg.npieces - 1 ? cfg.L - 1
+                                                 : (int)((((long long)(j + 1) * cfg.Lm1) - 1) / cfg.npieces);
         }
         alloc((void **)&h->piece_bounds_dev, pb.size() * sizeof(int));
         if (e == cudaSuccess) e = cudaMemcpy(h->piece_bounds_dev, pb.data(), pb.size() * sizeof(int), cudaMemcpyHostToDevice);
         cfg.piece_bounds = h->piece_bounds_dev;
         cfg.per_piece = (float)((double)cfg.Lm1 / (double)cfg.npieces);
+        cfg.inv_per_piece = (float)((double)cfg.npieces / (double)cfg.Lm1);
     }
     h->cfg = cfg;
     if (e != cudaSuccess) {

@@ -77,8 +77,8 @@ struct DevCfg {
     int block_bytes;          // bytes of one 32-env block
     int off_idx, off_wa, off_wb;  // byte offsets of the idx / wind A / wind B sections inside a block
     const double *basis;      // [npieces][4][fp] cardinal not-a-knot spline basis
-    const int *piece_bounds;  // [npieces][2] first / last wind sample index that falls into each spline piece
-    float per_piece;          // Lm1 / npieces: wind samples per spline piece
+    const int *piece_bounds;  // [npieces][2] first / last wind sample index that piece_of() assigns to each spline piece
+    float per_piece, inv_per_piece;  // Lm1 / npieces: wind samples per spline piece, and its reciprocal
     double *counters;         // [kCounterSlots][kNumCounters]
     const int32_t *ovr_s_y;   // optional episode-draw overrides (validation)
     const double *ovr_knots;

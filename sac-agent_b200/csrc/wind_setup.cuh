@@ -37,16 +37,6 @@ __device__ __forceinline__ void piece_of(const DevCfg &c, int index, int &j, int
     r = (int)(num - q * (uint32_t)c.Lm1);
 }
 
-// Value of sample `index` of curve `curve` before renormalisation (fp64 Horner on the piece table).
-__device__ __forceinline__ double eval_sample(const DevCfg &c, const double *coef, int curve, int index) {
-    index = max(0, min(index, c.L - 1));
-    int j, r;
-    piece_of(c, index, j, r);
-    const double s = (double)r * c.inv_Lm1;
-    const double *cf = coef + (curve * c.npieces + j) * 4;
-    return fma(fma(fma(cf[3], s, cf[2]), s, cf[1]), s, cf[0]);
-}
-
 // Called by all 32 lanes with warp-uniform arguments.  On return scratch[m] (m = 0..3) holds
 // the folded coefficients of the first drawn curve's piece containing sample `index_next`
 // (exp 4/6: velocity, exp 5: the rect source) and scratch[4 + m] those of the second drawn
@@ -96,31 +86,29 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
     __syncwarp();
 
     // --- extremal samples of every piece (np.min / np.max of wind.py:87-89) -----------------
-    // The discrete extremes of a piece sit at its end samples or next to a root of the derivative;
-    // the roots are LOCATED in fp32 (a 4-sample window absorbs the location error), the candidate
-    // samples are EVALUATED in fp64.
+    // The discrete extremes of the curve sit at the first / last sample of a piece or next to a root of
+    // the derivative.  Every lane looks only at the samples of ITS piece (evaluated from registers with
+    // the same piece and local coordinate the step kernel will use): a neighbour on the far side of a
+    // piece boundary is that piece's own first / last sample.  Roots are LOCATED in fp32 -- a 4-sample
+    // window absorbs the location error -- candidates are EVALUATED in fp64.
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     double mn = inf, mx = -inf;
     if (cv < nc && sub < np) {
         const double *cf = coef + (cv * np + sub) * 4;
         const double k0 = cf[0], k1 = cf[1], k2 = cf[2], k3 = cf[3];
+        const int first = __ldg(c.piece_bounds + 2 * sub), last = __ldg(c.piece_bounds + 2 * sub + 1);
         const int r_base = sub * c.Lm1;
+        const bool has_samples = first <= last;  // a table shorter than the spline can leave a piece without samples
         auto consider = [&](int index) {
-            // samples inside this lane's own piece (the usual case) are evaluated from registers, exactly as
-            // eval_sample would (same piece, same s); neighbours in other pieces take the table path
-            const int r = index * np - r_base;
-            double v;
-            if (index >= 0 && index < c.L && r >= 0 && r < c.Lm1) {
-                const double sl = (double)r * c.inv_Lm1;
-                v = fma(fma(fma(k3, sl, k2), sl, k1), sl, k0);
-            } else {
-                v = eval_sample(c, coef, cv, index);
-            }
+            if (!has_samples) return;
+            index = max(first, min(index, last));
+            const double sl = (double)(index * np - r_base) * c.inv_Lm1;
+            const double v = fma(fma(fma(k3, sl, k2), sl, k1), sl, k0);
             mn = (v < mn) ? v : mn;  // no NaNs here: plain compares instead of fmin / fmax
             mx = (v > mx) ? v : mx;
         };
-        consider(__ldg(c.piece_bounds + 2 * sub));      // first sample that falls into this piece
-        consider(__ldg(c.piece_bounds + 2 * sub + 1));  // last one
+        consider(first);
+        consider(last);
         const float A = 3.0f * (float)k3, B = 2.0f * (float)k2, C0 = (float)k1;
         const float nanf_ = __int_as_float(0x7fc00000);
         float s1 = nanf_, s2 = nanf_;
@@ -134,7 +122,7 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
         } else if (B != 0.0f) {
             s1 = __fdividef(-C0, B);
         }
-        const float per_piece = c.per_piece, margin = 3.0f / per_piece;
+        const float per_piece = c.per_piece, margin = 3.0f * c.inv_per_piece;
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
             const float sr = which ? s2 : s1;
