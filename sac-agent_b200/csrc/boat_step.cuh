@@ -562,9 +562,15 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             }
         };
 
+        // per-sub-step actions ([K][N] layout): the action of sub-step k + 1 is fetched while sub-step k computes
+        const bool per_substep = KMULTI && a.action_stride != 0;
+        const T *act_i = act + min(i, n_end - 1);
+        T action_k1 = action;
+        if (per_substep && ksteps > 1) action_k1 = __ldcs(act_i + (size_t)a.action_stride);
         for (int k = 0; k < ksteps; ++k) {
-            if (KMULTI) {
-                if (k > 0 && a.action_stride != 0) action = __ldcs(act + (size_t)k * (size_t)a.action_stride + min(i, n_end - 1));
+            if (KMULTI && k > 0) {
+                action = action_k1;
+                if (per_substep && k + 1 < ksteps) action_k1 = __ldcs(act_i + (size_t)(k + 1) * (size_t)a.action_stride);
             }
             bool need_setup = false;
             if (alive) {
