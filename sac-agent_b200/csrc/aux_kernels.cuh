@@ -50,11 +50,14 @@ __global__ void __launch_bounds__(kTile) boat_reset_kernel(const __grid_constant
     }
 }
 
+#ifndef BOAT_SETUPQ_MINBLOCKS
+#define BOAT_SETUPQ_MINBLOCKS 4
+#endif
 // Follow-up of a K > 1 step launch: the episode-end queue (one region per step CTA) is drained at full
 // occupancy -- one warp-cooperative wind setup per entry, the new episode's first-piece coefficients go
 // straight into the env's state block.  Warps are dealt to regions round-robin.
 template <typename T>
-__global__ void __launch_bounds__(kTile, 3) boat_setup_queue_kernel(const __grid_constant__ DevCfg c,
+__global__ void __launch_bounds__(kTile, BOAT_SETUPQ_MINBLOCKS) boat_setup_queue_kernel(const __grid_constant__ DevCfg c,
                                                                    const uint2 *__restrict__ entries,
                                                                    const unsigned *__restrict__ counts, int n_regions,
                                                                    int cap, int warps_per_region) {
