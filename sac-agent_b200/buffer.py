@@ -105,12 +105,25 @@ class ReplayBuffer:
                 r.double().cpu().numpy(), s2.double().cpu().numpy().reshape(-1, *self.input_shape),
                 d.cpu().numpy().astype(bool))
 
-    def sample_buffer(self, batch_size, as_torch=None, return_indices=False):
-        """buffer.py:24-35: uniform with replacement over [0, min(mem_cntr, mem_size))."""
+    def sample_buffer(self, batch_size, as_torch=None, return_indices=False, out=None):
+        """buffer.py:24-35: uniform with replacement over [0, min(mem_cntr, mem_size)).
+        ``out`` = (states, actions, rewards, states_, dones-as-uint8) device tensors to fill in place
+        (a learner's static batch: no allocation, nothing but the gather kernel is launched); they
+        are returned as they are."""
         torch = _torch()
         batch = int(batch_size)
         if self.mem_cntr == 0:
             raise ValueError("a must be non-empty")  # np.random.choice(0, n)
+        if out is not None:
+            s, a, r, s2, d = out
+            if (s.shape[0] != batch or s.dtype != self.dtype or d.dtype != torch.uint8
+                    or not all(t.is_contiguous() and t.device == self.device for t in out)):
+                raise ValueError("out: five contiguous tensors on the buffer's device, dtype of the buffer / uint8")
+            _lib.check(self._L.boatreplay_sample(self._h, batch, self.seed, self._samples, s.data_ptr(), a.data_ptr(),
+                                                 r.data_ptr(), s2.data_ptr(), d.data_ptr(), None, self._stream()),
+                       "boatreplay_sample")
+            self._samples += 1
+            return out
         s, a, r, s2, d = self._outputs(batch)
         idx = torch.empty(batch, dtype=torch.int64, device=self.device) if return_indices else None
         _lib.check(self._L.boatreplay_sample(self._h, batch, self.seed, self._samples, s.data_ptr(), a.data_ptr(),

@@ -1,0 +1,282 @@
+"""Device-resident mirror of the reference's SAC-v1 agent (agent/continuous_agent.py:9-154,
+agent/base_agent.py:3-19) -- SURVEY.md 8(f) rank 1, BASELINE.json configs[4].
+
+Same constructor, attributes and methods as the reference (`choose_action`, `remember`, `learn`,
+`update_network_parameters`, `save_models`, `load_models`, `memory`, `actor`, `critic_1`,
+`critic_2`, `value`, `target_value`), same update rule and hyper-parameters.  What changes is where
+the data lives and how the update is driven:
+
+* the replay memory is libboatenv's device ring (buffer.py); `learn()` gathers its batch with the
+  sample kernel straight into the learner's static input tensors -- no host round trip, no H2D
+  copies (the reference does five per update, continuous_agent.py:103-107);
+* the update of one `learn()` is ONE CUDA-graph launch: the three forward/backward passes, the fused
+  Adam step and the Polyak update are captured once and replayed (about 150 small kernels
+  whose launch latency otherwise dominates a 1024 x 256 update); batch and Gaussian draws are static
+  inputs of the graph;
+* `choose_action` takes the [N, 11] observation tensor of a BatchedBoatEnv and returns [N, 1]
+  actions without leaving the GPU (the reference syncs one action per env step through
+  `.cpu().numpy()`, continuous_agent.py:61); a numpy observation of one env still works and
+  returns a numpy action like the reference.
+
+`SACLearner` is the update rule on plain tensors (any torch device): the parity tests drive it with
+the batch, initial weights and Gaussian draws of a recorded run of the reference's own `learn()`.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .buffer import ReplayBuffer
+from .networks import ActorNetwork, CriticNetwork, ValueNetwork
+
+
+class SACLearner:
+    """The five networks, their Adam optimisers and one SAC-v1 update (continuous_agent.py:96-154)."""
+
+    def __init__(self, input_dims, n_actions, max_action, alpha, beta, gamma, tau, reward_scale, experiment_dir=None,
+                 device="cuda", capturable=False):
+        self.device = torch.device(device)
+        self.gamma, self.tau, self.scale = float(gamma), float(tau), float(reward_scale)
+        d = tuple(input_dims)
+        # creation order = the reference's (continuous_agent.py:19-52): identical torch seeds give identical weights
+        self.actor = ActorNetwork(experiment_dir, d, max_action, n_actions=n_actions, name="actor_network")
+        self.critic_1 = CriticNetwork(experiment_dir, d, n_actions, name="critic_network_1")
+        self.critic_2 = CriticNetwork(experiment_dir, d, n_actions, name="critic_network_2")
+        self.value = ValueNetwork(experiment_dir, d, name="value_network")
+        self.target_value = ValueNetwork(experiment_dir, d, name="target_value_network")
+        for net in self.networks():
+            net.to(self.device)
+        on_gpu = self.device.type == "cuda"
+        kw = dict(capturable=capturable, fused=True) if on_gpu else {}
+        # The reference keeps one Adam per network (networks.py:31,88,121) and steps them at three points of
+        # learn().  Nothing computed after a step reads the stepped weights (the critics are stepped last, the
+        # value net is only read again by the Polyak update), so ONE Adam over two learning-rate groups,
+        # stepped once after the three backward passes, is the same arithmetic in two kernel launches.
+        self._actor_params = list(self.actor.parameters())
+        self._critic_params = list(self.critic_1.parameters()) + list(self.critic_2.parameters())
+        self._value_params = list(self.value.parameters())
+        self.optimizer = torch.optim.Adam([{"params": self._actor_params, "lr": alpha},
+                                           {"params": self._critic_params + self._value_params, "lr": beta}], **kw)
+        for p in self.target_value.parameters():
+            p.requires_grad_(False)
+        self.update_network_parameters(tau=1.0)  # continuous_agent.py:55
+
+    def networks(self):
+        return (self.actor, self.critic_1, self.critic_2, self.value, self.target_value)
+
+    @torch.no_grad()
+    def update_network_parameters(self, tau=None):
+        """target = tau * value + (1 - tau) * target (continuous_agent.py:66-80)."""
+        tau = self.tau if tau is None else float(tau)
+        tgt, src = list(self.target_value.parameters()), list(self.value.parameters())
+        if tau == 1.0:
+            torch._foreach_copy_(tgt, src)
+            return
+        torch._foreach_mul_(tgt, 1.0 - tau)
+        torch._foreach_add_(tgt, src, alpha=tau)
+
+    def update(self, state, action, reward, new_state, done, eps_sample=None, eps_rsample=None):
+        """One update on a batch (state [B, obs], action [B, n_actions], reward [B], new_state [B, obs],
+        done [B] bool).  eps_*: optional standard-normal draws for the two `sample_normal` calls.
+        Returns (value_loss, actor_loss, critic_loss) as 0-d tensors."""
+        with torch.no_grad():
+            value_ = self.target_value(new_state).view(-1)
+            value_ = torch.where(done, torch.zeros_like(value_), value_)        # value_[done] = 0.0   (:111)
+            q_hat = self.scale * reward + self.gamma * value_                     # :141
+            # value target: a fresh non-reparameterised action under the current critics (:113-124).  The
+            # reference leaves this target attached to the graph, but every gradient it sends to the
+            # actor and the critics is zeroed before their own backward passes (:134, :138-139)
+            actions, log_probs = self.actor.sample_normal(state, reparameterize=False, eps=eps_sample)
+            critic_value = torch.min(self.critic_1(state, actions), self.critic_2(state, actions)).view(-1)
+            value_target = critic_value - log_probs.view(-1)
+        value = self.value(state).view(-1)
+        value_loss = 0.5 * F.mse_loss(value, value_target)
+        grads_v = torch.autograd.grad(value_loss, self._value_params)
+
+        actions, log_probs = self.actor.sample_normal(state, reparameterize=True, eps=eps_rsample)  # :127-136
+        critic_value = torch.min(self.critic_1(state, actions), self.critic_2(state, actions)).view(-1)
+        actor_loss = torch.mean(log_probs.view(-1) - critic_value)
+        # only the actor's gradients: what this loss sends into the critics is discarded by the reference too (:138-139)
+        grads_a = torch.autograd.grad(actor_loss, self._actor_params)
+
+        q1_old = self.critic_1(state, action).view(-1)                          # :138-152
+        q2_old = self.critic_2(state, action).view(-1)
+        critic_loss = 0.5 * F.mse_loss(q1_old, q_hat) + 0.5 * F.mse_loss(q2_old, q_hat)
+        grads_c = torch.autograd.grad(critic_loss, self._critic_params)
+
+        for p, g in zip(self._value_params + self._actor_params + self._critic_params, grads_v + grads_a + grads_c):
+            p.grad = g
+        self.optimizer.step()
+        self.update_network_parameters()                                        # :154
+        return value_loss.detach(), actor_loss.detach(), critic_loss.detach()
+
+
+class ContinuousAgent:
+    """agent/continuous_agent.py:9-154 on the GPU-resident env and replay ring."""
+
+    def __init__(self, config, experiment_dir, input_dims, env, device=None, seed=0, use_cuda_graph=True,
+                 memory=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("sac_agent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.env = env
+        self.config = config
+        a = config.agent
+        self.gamma, self.tau, self.scale = a.gamma, a.tvn_parameter_modulation_tau, a.reward_scale
+        self.batch_size = int(a.batch_size)
+        self.input_dims = tuple(input_dims)
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.memory = memory if memory is not None else ReplayBuffer(
+            a.max_size, self.input_dims, self.get_n_actions(), precision="fp32", device=self.device.index, seed=seed,
+            as_torch=True)
+        self.learner = SACLearner(self.input_dims, self.get_n_actions(), self.get_max_actions(), a.learning_rate_alpha,
+                                  a.learning_rate_beta, a.gamma, a.tvn_parameter_modulation_tau, a.reward_scale,
+                                  experiment_dir=experiment_dir, device=self.device, capturable=bool(use_cuda_graph))
+        L = self.learner
+        self.actor, self.critic_1, self.critic_2 = L.actor, L.critic_1, L.critic_2
+        self.value, self.target_value = L.value, L.target_value
+        self.use_cuda_graph = bool(use_cuda_graph)
+        B, O, A = self.batch_size, int(np.prod(self.input_dims)), self.get_n_actions()
+        kw = dict(dtype=torch.float32, device=self.device)
+        # static inputs of the captured update: sample_buffer writes them in place
+        self._batch = (torch.zeros((B, O), **kw), torch.zeros((B, A), **kw), torch.zeros(B, **kw),
+                       torch.zeros((B, O), **kw), torch.zeros(B, dtype=torch.uint8, device=self.device))
+        self._eps = torch.zeros((2, B, A), **kw)  # the Gaussian draws of the two sample_normal calls of one update
+        self._graph = None
+        self._losses = None
+        self._act_graphs = {}
+        self.updates = 0
+
+    # -- base_agent.py:7-19 -------------------------------------------------------------
+    def get_n_actions(self):
+        space = self.env.action_space
+        return space.shape[0] if hasattr(space, "shape") and hasattr(space, "high") else space.n
+
+    def get_max_actions(self):
+        space = self.env.action_space
+        if hasattr(space, "high"):
+            return space.high
+        raise NotImplementedError
+
+    # -- acting ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def choose_action(self, observation):
+        """continuous_agent.py:57-61.  A torch tensor [N, obs] (a BatchedBoatEnv's `obs`) gives a device
+        tensor [N, n_actions]; a numpy observation of ONE env gives a numpy action like the reference."""
+        if isinstance(observation, torch.Tensor):
+            obs = observation.to(device=self.device, dtype=torch.float32)
+            return self.actor.sample_normal(obs.reshape(-1, *self.input_dims), reparameterize=False)[0]
+        state = torch.as_tensor(np.array([observation]), dtype=torch.float32, device=self.device)
+        actions, _ = self.actor.sample_normal(state, reparameterize=False)
+        return actions.cpu().numpy()[0]
+
+    def choose_action_graphed(self, observation):
+        """`choose_action` for a PERSISTENT observation tensor (BatchedBoatEnv.obs): the policy's forward
+        pass is captured once per tensor and replayed; the result lives in a static output tensor."""
+        key = (observation.data_ptr(), tuple(observation.shape))
+        entry = self._act_graphs.get(key)
+        if entry is None:
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.choose_action(observation)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.choose_action(observation)
+            entry = self._act_graphs[key] = (g, out)
+        entry[0].replay()
+        return entry[1]
+
+    def remember(self, state, action, reward, new_state, done):
+        """continuous_agent.py:63-64: one transition, or N of them (leading batch dimension)."""
+        if np.ndim(reward) == 0:
+            self.memory.store_transition(state, action, reward, new_state, done)
+        else:
+            self.memory.store_batch(state, action, reward, new_state, done)
+
+    def step_and_remember(self, env, actions, done_flag_mode=1):
+        """main.py:81-88 for every env in one kernel: env.step + remember (ReplayBuffer.step_store)."""
+        return self.memory.step_store(env, actions, done_flag_mode=done_flag_mode)
+
+    # -- learning -------------------------------------------------------------------------
+    def _update_static(self):
+        s, a, r, s2, d = self._batch
+        return self.learner.update(s, a, r, s2, d.bool(), eps_sample=self._eps[0], eps_rsample=self._eps[1])
+
+    def _run_update(self):
+        if not self.use_cuda_graph:
+            self._losses = self._update_static()
+        else:
+            if self._graph is None:
+                self._capture()
+            self._graph.replay()
+        self.updates += 1
+        return self._losses
+
+    def learn(self):
+        """continuous_agent.py:96-154.  Returns None before the memory holds one batch (like the
+        reference); afterwards the three losses (value, actor, critic) as device tensors (no sync).
+        Three launches: the sample-gather kernel, the Gaussian draws, the captured update."""
+        if self.memory.mem_cntr < self.batch_size:
+            return None
+        self.memory.sample_buffer(self.batch_size, as_torch=True, out=self._batch)
+        self._eps.normal_()
+        return self._run_update()
+
+    def learn_from(self, state, action, reward, new_state, done, eps=None):
+        """One update on a caller-supplied batch (device or host arrays of the batch size); `eps`
+        [2, B, n_actions] prescribes the Gaussian draws (parity tests), else they are drawn here."""
+        for dst, src in zip(self._batch, (state, action, reward, new_state, done)):
+            dst.copy_(torch.as_tensor(src).reshape(dst.shape))
+        if eps is None:
+            self._eps.normal_()
+        else:
+            self._eps.copy_(torch.as_tensor(eps).reshape(self._eps.shape))
+        return self._run_update()
+
+    def _capture(self):
+        """Capture one update into a CUDA graph.  Gradients and Adam's state must exist (as the tensors the
+        graph will keep using) before capture, so three throw-away eager updates run first on a side
+        stream; weights and optimiser state are then put back, i.e. every `learn()` -- the first one
+        included -- is exactly one update."""
+        L = self.learner
+        opts = (L.optimizer,)
+        params = [p for net in L.networks() for p in net.parameters()]
+        saved_params = [p.detach().clone() for p in params]
+        saved_state = {}
+        for opt in opts:
+            for group in opt.param_groups:
+                for p in group["params"]:
+                    st = opt.state.get(p)
+                    saved_state[p] = None if not st else {k: v.clone() for k, v in st.items() if torch.is_tensor(v)}
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._update_static()
+            with torch.no_grad():
+                torch._foreach_copy_(params, saved_params)
+                for opt in opts:
+                    for group in opt.param_groups:
+                        for p in group["params"]:
+                            for k, v in opt.state[p].items():
+                                if torch.is_tensor(v):
+                                    v.zero_() if saved_state[p] is None else v.copy_(saved_state[p][k])
+        cur.wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._losses = self._update_static()
+
+    def update_network_parameters(self, tau=None):
+        self.learner.update_network_parameters(tau)
+
+    def save_models(self):
+        for net in self.learner.networks():
+            net.save_checkpoint()
+
+    def load_models(self):
+        for net in self.learner.networks():
+            net.load_checkpoint()

@@ -1,0 +1,168 @@
+"""SAC update parity: `SACLearner` / `ContinuousAgent` against the recorded run of
+the reference's own `ContinuousAgent.learn()` (tests/golden/agent_update.npz, written by
+oracle/make_agent_golden.py from agent/continuous_agent.py:96-154 + networks/networks.py).
+
+Tolerances (fp32 learner against an fp32 reference on another BLAS): gradients 2e-4 of the tensor's
+largest gradient, weights 1e-6 + 2 % of the learning rate -- the first Adam steps move every weight by
+~lr * sign(g), so a weight whose gradient is within rounding of zero may differ by a fraction of lr;
+at most 0.2 % of the sampled positions may exceed that (none do on the CPU).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import make_agent_golden as G  # noqa: E402  (test infrastructure)
+from oracle import ref_shim as R  # noqa: E402
+
+import sac_agent_b200 as S  # noqa: E402
+from sac_agent_b200.continuous_agent import ContinuousAgent, SACLearner  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "agent_update.npz")
+
+
+def _learner(meta, device, capturable=False):
+    L = SACLearner((11,), 1, np.array([1.0], dtype=np.float32), float(meta["meta/learning_rate_alpha"]),
+                   float(meta["meta/learning_rate_beta"]), float(meta["meta/gamma"]),
+                   float(meta["meta/tvn_parameter_modulation_tau"]), float(meta["meta/reward_scale"]),
+                   device=device, capturable=capturable)
+    return L
+
+
+def _load_init(L, seed):
+    w0 = G.init_weights(seed)
+    for n in G.NETS:
+        getattr(L, n).load_state_dict({k: torch.from_numpy(v.copy()) for k, v in w0[n].items()})
+
+
+def _compare(rec, L, u, lr_of):
+    bad = []
+    for n in G.NETS:
+        net = getattr(L, n)
+        for k, p in net.named_parameters():
+            for kind in ("w", "g"):
+                key = f"u{u}/{n}/{k}/{kind}"
+                if key + "@" not in rec:
+                    continue
+                t = p if kind == "w" else p.grad
+                ours = t.detach().float().cpu().numpy().reshape(-1)
+                pos = G.sample_positions(tuple(p.shape), key)
+                ref = rec[key + "@"]
+                got = ours[pos]
+                if kind == "g":
+                    tol = 2e-4 * max(np.abs(ref).max(), 1e-12) + 1e-9
+                else:
+                    tol = 1e-6 + 0.02 * lr_of[n]
+                frac = np.mean(np.abs(got - ref) > tol)
+                if frac > 0.002:
+                    bad.append((key, float(np.abs(got - ref).max()), tol, float(frac)))
+                # the whole tensor through its recorded norm
+                l2 = float(np.sqrt((ours.astype(np.float64) ** 2).sum()))
+                assert abs(l2 - float(rec[key + "#l2"])) <= 1e-3 * max(float(rec[key + "#l2"]), 1e-9), key
+    assert not bad, bad
+
+
+def _run(rec, device, via_agent=False):
+    seed, n_updates, batch = int(rec["meta/seed"]), int(rec["meta/n_updates"]), int(rec["meta/batch"])
+    b, noise = G.make_batch(seed, batch), G.make_noise(seed, n_updates, batch)
+    lr_of = {"actor": float(rec["meta/learning_rate_alpha"])}
+    for n in ("critic_1", "critic_2", "value", "target_value"):
+        lr_of[n] = float(rec["meta/learning_rate_beta"])
+    if via_agent:
+        cfg = S.load_config()
+        env = type("E", (), {"action_space": S.Box(low=-1, high=1, dtype=np.float32)})()
+        mem = S.ReplayBuffer(4096, (11,), 1, precision="fp32", device=0, as_torch=True)
+        agent = ContinuousAgent(cfg, None, (11,), env, device=0, use_cuda_graph=True, memory=mem)
+        L = agent.learner
+    else:
+        agent = None
+        L = _learner(rec, device)
+    _load_init(L, seed)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in b.items()}
+    for u in range(1, n_updates + 1):
+        if via_agent:
+            agent.learn_from(t["state"], t["action"], t["reward"], t["new_state"], t["done"].to(torch.uint8),
+                             eps=torch.from_numpy(noise[u - 1]))
+        else:
+            e = torch.from_numpy(noise[u - 1]).to(device)
+            L.update(t["state"], t["action"], t["reward"], t["new_state"], t["done"], eps_sample=e[0], eps_rsample=e[1])
+        if u in rec["meta/record_after"]:
+            _compare(rec, L, u, lr_of)
+    if via_agent:
+        assert agent.updates == n_updates
+        mem.close()
+
+
+def test_state_dict_layout_matches_reference():
+    rec = np.load(GOLDEN)
+    L = _learner(rec, "cpu")
+    ours = [f"{n}/{k}/{tuple(p.shape)}" for n in G.NETS for k, p in getattr(L, n).named_parameters()]
+    assert ours == [str(x) for x in rec["meta/param_names"]]
+    for p, q in zip(L.value.parameters(), L.target_value.parameters()):  # update_network_parameters(tau=1)
+        assert torch.equal(p, q)
+
+
+def test_learner_cpu_matches_recorded_reference_update():
+    _run(np.load(GOLDEN), "cpu")
+
+
+@pytest.mark.skipif(not R.reference_available(), reason="reference not mounted (GPU box)")
+def test_learner_cpu_matches_live_reference_on_a_fresh_seed():
+    rec = G.reference_learn(seed=11, n_updates=2, batch=256, record_after=(2,))
+    _run(rec, "cpu")
+
+
+def test_agent_needs_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    env = type("E", (), {"action_space": S.Box(low=-1, high=1, dtype=np.float32)})()
+    with pytest.raises(RuntimeError):
+        ContinuousAgent(S.load_config(), None, (11,), env)
+
+
+@pytest.mark.gpu
+def test_learner_gpu_matches_recorded_reference_update():
+    _run(np.load(GOLDEN), "cuda")
+
+
+@pytest.mark.gpu
+def test_agent_cuda_graph_matches_recorded_reference_update():
+    _run(np.load(GOLDEN), "cuda", via_agent=True)
+
+
+@pytest.mark.gpu
+def test_agent_api_on_batched_env():
+    """choose_action / step_and_remember / learn on a BatchedBoatEnv, single-env numpy API, checkpoints."""
+    import tempfile
+    cfg = S.load_config(base_settings__experiment=6, agent__batch_size=256)
+    env = S.BatchedBoatEnv(cfg, 2048, seed=3, precision="fp32", device=0, auto_reset=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        agent = ContinuousAgent(cfg, tmp, env.observation_space.shape, env, device=0, seed=3)
+        assert agent.get_n_actions() == 1 and float(agent.get_max_actions()[0]) == 1.0
+        obs = env.reset()
+        assert agent.learn() is None  # memory below one batch: continuous_agent.py:97-98
+        for it in range(6):
+            a = agent.choose_action_graphed(obs)
+            assert a.shape == (2048, 1) and float(a.abs().max()) <= 1.0
+            agent.step_and_remember(env, a.squeeze(-1))
+            losses = agent.learn()
+        assert agent.memory.mem_cntr == 6 * 2048 and agent.updates == 6
+        assert all(torch.isfinite(x).item() for x in losses)
+        a1 = agent.choose_action(np.zeros(11))  # the reference's single-observation call
+        assert isinstance(a1, np.ndarray) and a1.shape == (1,)
+        before = [p.detach().clone() for p in agent.actor.parameters()]
+        agent.save_models()
+        assert sorted(os.listdir(os.path.join(tmp, "checkpoints"))) == sorted(
+            ["actor_network", "critic_network_1", "critic_network_2", "value_network", "target_value_network"])
+        with torch.no_grad():
+            for p in agent.actor.parameters():
+                p.add_(1.0)
+        agent.load_models()
+        assert all(torch.equal(p, q) for p, q in zip(agent.actor.parameters(), before))
+        agent.learn()  # the captured graph still works on the reloaded (same-storage) parameters
+    env.close()
+    agent.memory.close()

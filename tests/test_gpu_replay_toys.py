@@ -209,5 +209,6 @@ def test_end_to_end_sac_loop_smoke(S):
     spec = importlib.util.spec_from_file_location("train_sac", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    losses = mod.main(["--envs", "4096", "--iters", "30", "--buffer", "65536", "--log-every", "30"])
-    assert all(math.isfinite(x) for x in losses)
+    out = mod.main(["--envs", "4096", "--iters", "30", "--warmup-iters", "5", "--buffer", "65536", "--log-every", "30"])
+    assert all(math.isfinite(x) for x in out["losses_v_pi_q"])
+    assert out["env_steps_per_s"] > 0 and out["cuda_graph"]
