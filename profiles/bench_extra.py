@@ -96,6 +96,9 @@ def main():
         boat_case("exp6_fp32_16M_k8_long_episodes", 6, "fp32", 16 * M, 0.02, 4 + 5 + (112 + 44) / 8, 30, 30, k=8)
         boat_case("exp6_fp32_16M_k1_long_episodes", 6, "fp32", 16 * M, 0.02, 165, 100, 100)
         return
+    if os.environ.get("BENCH_EXTRA_ONLY") == "replay":
+        replay_cases(M)
+        return
     # BASELINE.json configs[1]: exp 3, 4096 envs, fp64 (launch-latency bound at this size) and the same at 4M envs
     boat_case("exp3_fp64_4096", 3, "fp64", 4096, 0.05, 249, 50, 200)
     boat_case("exp3_fp64_4M", 3, "fp64", 4 * M, 0.05, 249, 50, 50)
@@ -112,7 +115,20 @@ def main():
     boat_case("exp6_fp32_16M_k8_long_episodes", 6, "fp32", 16 * M, 0.02, 4 + 5 + (112 + 44) / 8, 30, 30, k=8)
     boat_case("exp6_fp32_16M_k1_long_episodes", 6, "fp32", 16 * M, 0.02, 165, 100, 100)
 
-    # replay buffer: batched store, sample-gather (agent/buffer.py), fused step+store
+    replay_cases(M)
+
+    # toy envs, 1M envs each, fp32 (BASELINE.json configs[3]): k iterations per launch
+    car = S.ToyCar(n_envs=M, jitter=0.1, seed=0, precision="fp32", device=0)
+    ms = timed(lambda: car.step(100), 20)
+    emit("toy_car_1M_k100", ms, M * 100, "env-iterations")
+    chute = S.ToyParachute(n_envs=M, jitter=0.1, seed=0, precision="fp32", device=0)
+    ms = timed(lambda: (chute.reset(), chute.step(100)), 20)
+    emit("toy_parachute_1M_k100", ms, M * 100, "env-iterations")
+    car.close(); chute.close()
+
+
+def replay_cases(M):
+    """replay buffer: batched store, sample-gather (agent/buffer.py), fused step+store"""
     n, cap = 4 * M, 16 * M
     buf = S.ReplayBuffer(cap, (11,), 1, precision="fp32", device=0, as_torch=True)
     s = torch.randn(n, 11, device="cuda")
@@ -125,6 +141,12 @@ def main():
         ms = timed(lambda: buf.sample_buffer(batch), 50)
         emit(f"replay_sample_gather_{batch}", ms, batch, "rows", 2 * 97,
              note="includes the torch.empty of the five output tensors; 97 B gathered + 97 B written per row")
+    for batch in (1024, 1 << 20):  # the learner's way: five preallocated outputs, nothing but the gather kernel
+        outs = buf.sample_buffer(batch)
+        outs = (outs[0], outs[1], outs[2], outs[3], outs[4].to(torch.uint8))
+        ms = timed(lambda: buf.sample_buffer(batch, out=outs), 50)
+        emit(f"replay_sample_gather_{batch}_into_static_batch", ms, batch, "rows", 2 * 97,
+             note="sample_buffer(out=...): 97 B gathered + 97 B written per row")
     cfg = S.load_config(base_settings__experiment=6)
     env = S.BatchedBoatEnv(cfg, 16 * M, seed=1, precision="fp32", device=0, auto_reset=True)
     env.reset()
@@ -144,15 +166,6 @@ def main():
     emit("exp6_fp32_16M_fused_step_store", ms, 16 * M, "env-steps", 165 + 44 + 97,
          note="step (165 B) + previous obs read (44 B) + transition written (97 B)")
     env.close(); big.close(); buf.close()
-
-    # toy envs, 1M envs each, fp32 (BASELINE.json configs[3]): k iterations per launch
-    car = S.ToyCar(n_envs=M, jitter=0.1, seed=0, precision="fp32", device=0)
-    ms = timed(lambda: car.step(100), 20)
-    emit("toy_car_1M_k100", ms, M * 100, "env-iterations")
-    chute = S.ToyParachute(n_envs=M, jitter=0.1, seed=0, precision="fp32", device=0)
-    ms = timed(lambda: (chute.reset(), chute.step(100)), 20)
-    emit("toy_parachute_1M_k100", ms, M * 100, "env-iterations")
-    car.close(); chute.close()
 
 
 if __name__ == "__main__":

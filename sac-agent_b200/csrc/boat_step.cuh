@@ -357,20 +357,24 @@ __device__ __forceinline__ bool queue_pop(SetupQueue *q, int n_producers, SetupR
 // scratch of the setup warps.
 template <typename T>
 struct WarpSmem {
-    int tile_off, scratch_off, bar_off, bytes;
-    __host__ __device__ WarpSmem(int block_bytes, int scratch_dbl) {
+    int tile_off, prev_off, scratch_off, bar_off, bytes;
+    // prev_tiles: 2 when the launch also stores the transition (fused agent.remember): double-buffered
+    // TMA staging of the PREVIOUS observation tile, which leaves again as the ring's `state` rows
+    __host__ __device__ WarpSmem(int block_bytes, int scratch_dbl, int prev_tiles) {
+        const int tile_bytes = 32 * kObsDim * (int)sizeof(T);  // 1408 / 2816: a multiple of 128
         tile_off = kStages * block_bytes;
-        scratch_off = tile_off + 32 * kObsDim * (int)sizeof(T);
+        prev_off = tile_off + tile_bytes;
+        scratch_off = prev_off + prev_tiles * tile_bytes;
         bar_off = scratch_off + scratch_dbl * 8;
-        bytes = (bar_off + kStages * 8 + 127) / 128 * 128;
+        bytes = (bar_off + (kStages + 2) * 8 + 127) / 128 * 128;
     }
 };
 template <typename T>
 struct CtaSmem {
     WarpSmem<T> warp;
     int queue_off, setup_scratch_off, setup_scratch_bytes, kq_off, bytes;
-    __host__ __device__ CtaSmem(int block_bytes, int ncurves, int npieces, int n_setup)
-        : warp(block_bytes, n_setup > 0 ? 0 : scratch_doubles(ncurves, npieces)) {
+    __host__ __device__ CtaSmem(int block_bytes, int ncurves, int npieces, int n_setup, bool fused_store)
+        : warp(block_bytes, n_setup > 0 ? 0 : scratch_doubles(ncurves, npieces), fused_store ? 2 : 0) {
         queue_off = kWarpsPerCta * warp.bytes;
         setup_scratch_off = queue_off + (n_setup > 0 ? (int)sizeof(SetupQueue) : 0);
         setup_scratch_bytes = (scratch_doubles(ncurves, npieces) * 8 + 127) / 128 * 128;
@@ -400,7 +404,8 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bb = c.block_bytes;
 
-    const CtaSmem<T> cta(bb, c.ncurves, c.npieces, kSetup);
+    const bool fused_store = !KMULTI && a.rp.state != nullptr;
+    const CtaSmem<T> cta(bb, c.ncurves, c.npieces, kSetup, fused_store);
     const WarpSmem<T> &lay = cta.warp;
     SetupQueue *queue = reinterpret_cast<SetupQueue *>(smem_raw + cta.queue_off);
     if (kSetup > 0) {
@@ -455,6 +460,8 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
     T *tile = reinterpret_cast<T *>(wbase + lay.tile_off);              // [32][11]
     double *scratch = reinterpret_cast<double *>(wbase + lay.scratch_off);
     uint64_t *full = reinterpret_cast<uint64_t *>(wbase + lay.bar_off);
+    uint64_t *pfull = full + kStages;                                   // [2] barriers of the previous-obs tiles
+    unsigned char *prev_base = wbase + lay.prev_off;                    // [2][kTileBytes]  (fused store only)
     T *row = tile + lane * kObsDim;
 
     // env indices of one handle fit 32 bits (checked at create).  The warp walks SEQUENCE numbers
@@ -476,9 +483,21 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
+        mbar_init(pfull, 1);
+        mbar_init(pfull + 1, 1);
         mbar_fence_init();
     }
     __syncwarp();
+    // fused store: the tile of observations the PREVIOUS step wrote for a (full) block is fetched one block
+    // ahead by a bulk copy of its own and leaves again as the ring's `state` rows without touching registers
+    const T *prev_obs = reinterpret_cast<const T *>(a.obs_in);
+    auto prev_prefetch = [&](int q, int buf) {  // lane 0 only
+        const int b = block_of(q);
+        if (b * 32 + 32 <= n_end) {
+            mbar_expect_tx(pfull + buf, (uint32_t)kTileBytes);
+            tma_load_1d(prev_base + buf * kTileBytes, prev_obs + (size_t)b * (32 * kObsDim), (uint32_t)kTileBytes, pfull + buf);
+        }
+    };
     if (lane == 0) {  // prologue: fill the pipeline
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
@@ -488,7 +507,10 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                 tma_load_1d(stage_base + s * bb, c.state + (size_t)block_of(q) * (size_t)bb, (uint32_t)bb, full + s);
             }
         }
+        if (fused_store) prev_prefetch(seq, 0);
     }
+    int pbuf = 0;            // previous-obs buffer of the current block
+    uint32_t pphase = 0u;    // bit b: parity the next wait on pfull[b] expects
     const T *act = reinterpret_cast<const T *>(a.actions);
     const T inv_Lm1 = sizeof(T) == 8 ? (T)c.inv_Lm1 : (T)c.f.inv_Lm1;
     const bool auto_reset = (a.flags & BOATENV_AUTO_RESET) != 0;
@@ -532,11 +554,12 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
         T rsum = (T)0;
         int code = BOATENV_TERM_NONE, nsteps = 0;
         bool alive = true, wind_dirty = false;
-        if (tile_in_flight) {  // the previous block's bulk stores must be done reading `tile`
+        if (tile_in_flight) {  // the previous block's bulk stores must be done reading `tile` (and its previous-obs buffer)
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
             tile_in_flight = false;
         }
+        if (fused_store && lane == 0 && seq + wstride < blk_end) prev_prefetch(seq + wstride, pbuf ^ 1);
         bool ring_in_flight = false;
         char *gb = c.state + (size_t)blk * (size_t)bb;
 
@@ -628,29 +651,27 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                 T *ring_n = reinterpret_cast<T *>(a.rp.new_state) + slot0 * kObsDim;
                 const bool bulk = rows_w == 32 && slot0 + 32 <= a.rp.mem_size &&
                                   ((reinterpret_cast<uintptr_t>(ring_s) | reinterpret_cast<uintptr_t>(ring_n)) & 15u) == 0;
-                if (bulk) {  // s' = the staged tile: one bulk store; s = last step's observation tile: 128-bit copy
+                const T *prev_tile = reinterpret_cast<const T *>(prev_base + pbuf * kTileBytes);
+                if (rows_w == 32) {  // a full block: its previous observations were prefetched into prev_tile
+                    mbar_wait(pfull + pbuf, (pphase >> pbuf) & 1u);
+                    pphase ^= 1u << pbuf;
+                }
+                if (bulk) {  // s' = the staged tile, s = the prefetched previous tile: two bulk stores, no registers
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
+                        tma_store_1d(ring_s, prev_tile, kTileBytes);
                         tma_store_1d(ring_n, tile, kTileBytes);
                         tma_store_commit();
                     }
                     ring_in_flight = true;
-                    using V = typename VecOf<T>::type;
-                    constexpr int NVEC = 32 * kObsDim / VecOf<T>::W;
-                    const V *pv = reinterpret_cast<const V *>(prev);
-                    V *rs = reinterpret_cast<V *>(ring_s);
-#pragma unroll
-                    for (int it = 0; it < (NVEC + 31) / 32; ++it) {
-                        const int v = lane + 32 * it;
-                        if (v < NVEC) rs[v] = __ldcs(pv + v);
-                    }
-                } else {
+                } else {  // ragged last block, ring wrap inside the block or unaligned ring: element-wise
+                    const T *src = rows_w == 32 ? prev_tile : prev;
                     for (int e = lane; e < rows_w * kObsDim; e += 32) {
                         const int rr = e / kObsDim, q = e - rr * kObsDim;
                         long long slot = a.rp.base_slot + (long long)blk * 32 + rr;
                         if (slot >= a.rp.mem_size) slot -= a.rp.mem_size;
-                        reinterpret_cast<T *>(a.rp.state)[slot * kObsDim + q] = prev[e];
+                        reinterpret_cast<T *>(a.rp.state)[slot * kObsDim + q] = src[e];
                         reinterpret_cast<T *>(a.rp.new_state)[slot * kObsDim + q] = tile[e];
                     }
                 }
@@ -780,6 +801,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             __syncwarp();
             for (int e = lane; e < rows * kObsDim; e += 32) gobs[e] = tile[e];
         }
+        pbuf ^= 1;
     }
     if (kSetup > 0) {
         __syncwarp();

@@ -21,7 +21,7 @@ static cudaError_t launch_step_wk(const DevCfg &c, const StepArgs &a_in, cudaStr
     auto kern = boat_step_kernel<REAL, WK, KMULTI>;
     constexpr int n_setup = setup_warps<WK, KMULTI>();
     constexpr int threads = kTile + 32 * n_setup;
-    const int smem = CtaSmem<REAL>(c.block_bytes, c.ncurves, c.npieces, n_setup).bytes;
+    const int smem = CtaSmem<REAL>(c.block_bytes, c.ncurves, c.npieces, n_setup, !KMULTI && a.rp.state != nullptr).bytes;
     static int cached_smem = -1, ctas_per_sm = 0, n_sm = 0, cached_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
