@@ -49,13 +49,25 @@ __device__ __forceinline__ void copy_flat(T *__restrict__ dst, const T *__restri
         const long long nvec = count / W;
         const V *sv = reinterpret_cast<const V *>(src);
         V *dv = reinterpret_cast<V *>(dst);
-        for (long long v = tid; v < nvec; v += nthreads) dv[v] = __ldcs(sv + v);
+        long long v = tid;
+#pragma unroll 1
+        for (; v + 3 * nthreads < nvec; v += 4 * nthreads) {  // four independent 128-bit loads in flight per thread
+            const V x0 = __ldcs(sv + v), x1 = __ldcs(sv + v + nthreads), x2 = __ldcs(sv + v + 2 * nthreads),
+                    x3 = __ldcs(sv + v + 3 * nthreads);
+            dv[v] = x0;
+            dv[v + nthreads] = x1;
+            dv[v + 2 * nthreads] = x2;
+            dv[v + 3 * nthreads] = x3;
+        }
+        for (; v < nvec; v += nthreads) dv[v] = __ldcs(sv + v);
         for (long long e = nvec * W + tid; e < count; e += nthreads) dst[e] = src[e];
     } else {
         for (long long e = tid; e < count; e += nthreads) dst[e] = __ldcs(src + e);
     }
 }
 
+// blockIdx.y picks the array (0 state, 1 new_state, 2 action, 3 reward, 4 terminal): every CTA runs one
+// flat copy loop, so the four loads in flight per thread cost a handful of registers.
 template <typename T>
 __global__ void __launch_bounds__(256) replay_store_kernel(
     T *__restrict__ state, T *__restrict__ new_state, T *__restrict__ action, T *__restrict__ reward,
@@ -64,12 +76,15 @@ __global__ void __launch_bounds__(256) replay_store_kernel(
     int obs_dim, int n_actions) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nthreads = (long long)gridDim.x * blockDim.x;
-    copy_flat<T>(state + slot0 * obs_dim, s + row0 * obs_dim, rows * obs_dim, tid, nthreads);
-    copy_flat<T>(new_state + slot0 * obs_dim, s2 + row0 * obs_dim, rows * obs_dim, tid, nthreads);
-    copy_flat<T>(action + slot0 * n_actions, a + row0 * n_actions, rows * n_actions, tid, nthreads);
-    copy_flat<T>(reward + slot0, r + row0, rows, tid, nthreads);
-    for (long long e = tid; e < rows; e += nthreads)
-        terminal[slot0 + e] = done[row0 + e] ? 1 : 0;  // np.zeros(..., bool) storage (buffer.py:11,20)
+    switch (blockIdx.y) {
+    case 0: copy_flat<T>(state + slot0 * obs_dim, s + row0 * obs_dim, rows * obs_dim, tid, nthreads); break;
+    case 1: copy_flat<T>(new_state + slot0 * obs_dim, s2 + row0 * obs_dim, rows * obs_dim, tid, nthreads); break;
+    case 2: copy_flat<T>(action + slot0 * n_actions, a + row0 * n_actions, rows * n_actions, tid, nthreads); break;
+    case 3: copy_flat<T>(reward + slot0, r + row0, rows, tid, nthreads); break;
+    default:
+        for (long long e = tid; e < rows; e += nthreads)
+            terminal[slot0 + e] = done[row0 + e] ? 1 : 0;  // np.zeros(..., bool) storage (buffer.py:11,20)
+    }
 }
 
 // np.random.choice(max_mem, batch) stand-in (buffer.py:27): draw b = word (b & 3) of
@@ -141,7 +156,7 @@ cudaError_t launch_store(boatreplay_t r, long long n, const void *s, const void 
         const long long rows = std::min(n - row0, r->mem_size - slot0);
         long long blocks = (rows * r->obs_dim / 4 + 255) / 256;
         blocks = std::max(1LL, std::min(blocks, 148LL * 8));
-        replay_store_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
+        replay_store_kernel<T><<<dim3((unsigned)blocks, 5), 256, 0, st>>>(
             (T *)r->state, (T *)r->new_state, (T *)r->action, (T *)r->reward, r->terminal, (const T *)s, (const T *)a,
             (const T *)rew, (const T *)s2, done, rows, row0, slot0, r->obs_dim, r->n_actions);
         count_launch();
