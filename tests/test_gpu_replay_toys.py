@@ -105,19 +105,25 @@ def test_replay_sample_semantics(S):
     buf.close(); twin.close()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp64"])
-def test_fused_step_store_equals_step_then_store(S, precision):
-    """env.step + agent.remember (main.py:81-88) in one kernel == the two-call sequence."""
+@pytest.mark.parametrize("precision,n,T,cap,scale", [
+    ("fp32", 3000, 60, 8192, 3.0), ("fp64", 3000, 60, 8192, 3.0),   # one state block per warp, ragged last block
+    # several blocks per persistent warp (the double-buffered previous-obs prefetch runs ahead), bulk path:
+    ("fp32", 200_016, 10, 500_000, 6.0),
+    # the same with ring slots that break the 16-byte alignment of the bulk stores (element-wise path):
+    ("fp32", 200_003, 10, 500_001, 6.0), ("fp64", 100_003, 8, 300_001, 6.0),
+])
+def test_fused_step_store_equals_step_then_store(S, precision, n, T, cap, scale):
+    """env.step + agent.remember (main.py:81-88) in one kernel == the two-call sequence; the ring wraps
+    inside every run (n * T > cap)."""
     import torch
     cfg = S.load_config(base_settings__experiment=6)
-    n, T, cap = 3000, 60, 8192   # the ring wraps inside the run (3000 * 60 > 8192)
     e1 = S.BatchedBoatEnv(cfg, n, seed=8, precision=precision, device=0, auto_reset=True)
     e2 = S.BatchedBoatEnv(cfg, n, seed=8, precision=precision, device=0, auto_reset=True)
     b1 = S.ReplayBuffer(cap, (11,), 1, precision=precision, device=0, as_torch=True)
     b2 = S.ReplayBuffer(cap, (11,), 1, precision=precision, device=0, as_torch=True)
     e1.reset(); e2.reset()
     for t in range(T):
-        acts = e1.uniform_actions(t, 3.0)   # large steps: frequent rudder_broken -> resets in the window
+        acts = e1.uniform_actions(t, scale)   # large steps: frequent rudder_broken -> resets in the window
         prev = e1.obs.clone()
         o, r, d, info = e1.step(acts)
         # s' of a finished env is its TERMINAL observation, not the reset one
@@ -132,7 +138,7 @@ def test_fused_step_store_equals_step_then_store(S, precision):
     assert int(e1.counters()["episodes"]) > 0
     # done_flag_mode 0 stores done itself
     b3 = S.ReplayBuffer(cap, (11,), 1, precision=precision, device=0, as_torch=True)
-    b3.step_store(e2, e1.uniform_actions(T, 3.0), done_flag_mode=0)
+    b3.step_store(e2, e1.uniform_actions(T, scale), done_flag_mode=0)
     assert torch.equal(b3.gather(torch.arange(n, device="cuda"))[4], e2.done.bool())
     for x in (e1, e2, b1, b2, b3):
         x.close()
