@@ -125,7 +125,9 @@ BOATENV_API int boatenv_step_k(boatenv_t h, const void *actions, int64_t action_
  * copies obs/reward/done D2H, chunked over internal streams so that the copies overlap
  * the kernel.  Waits for all work queued on the device before it starts and blocks until
  * the results are in host memory.  This is the end-to-end
- * call a CPU-side agent loop (main.py:80-81) makes. */
+ * call a CPU-side agent loop (main.py:80-81) makes.  Up to 2048 envs (the reference's single-env
+ * loop included) it runs zero-copy instead: the kernel reads and writes mapped pinned memory
+ * directly, one launch and one synchronize per call. */
 BOATENV_API int boatenv_step_host(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host,
                       uint8_t *done_host, uint32_t flags);
 /* The same, also returning the termination codes (BOATENV_TERM_*) of this step in term_host: what the
@@ -144,6 +146,11 @@ enum boatenv_field {
 /* out / in: T[n_envs] for fields 0..7, uint32[n_envs] for fields 8..9 (device). */
 BOATENV_API int boatenv_get_field(boatenv_t h, int field, void *out, void *stream);
 BOATENV_API int boatenv_set_field(boatenv_t h, int field, const void *in, void *stream);
+
+/* All ten fields of ONE env (boatenv_field order, as doubles) into HOST memory with one launch:
+ * what `env.boat.s_x ... rudder_angle` of main.py:94 and `return_all_data` (boat_env.py:128-140,
+ * called by the Recorder every step, recorder.py:24-36) read.  Blocking. */
+BOATENV_API int boatenv_env_state_host(boatenv_t h, int64_t env_index, double *out_host /* [10] */);
 
 /* env.boat.wind.wind_velocity / .wind_angle (wind.py:16-17, recorder.py:46-47): the
  * current episode's tables of env `env_index`, double[L] each (device). */

@@ -42,6 +42,7 @@ SIGNATURES = {
     "boatenv_step_host_term": (C.c_int, [vp, vp, vp, vp, vp, vp, u32]),
     "boatenv_get_field": (C.c_int, [vp, C.c_int, vp, vp]),
     "boatenv_set_field": (C.c_int, [vp, C.c_int, vp, vp]),
+    "boatenv_env_state_host": (C.c_int, [vp, i64, C.POINTER(dbl)]),
     "boatenv_wind_table": (C.c_int, [vp, i64, vp, vp, vp]),
     "boatenv_wind_length": (C.c_int, [vp]),
     "boatenv_set_episode_draws": (C.c_int, [vp, vp, vp, vp]),

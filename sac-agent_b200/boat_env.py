@@ -281,8 +281,17 @@ class _BoatFacade:
         self.dt = cfg.base_settings.dt if hasattr(cfg, "base_settings") else cfg["base_settings"]["dt"]
         self.wind = _WindFacade(benv)
 
+        self._state = (C.c_double * 10)()
+        self._fresh = False   # BoatEnv.step / reset invalidate; the first attribute read refetches all ten
+
+    def invalidate(self):
+        self._fresh = False
+
     def _f(self, name):
-        return float(self._b.get_field(name)[0].item())
+        if not self._fresh:  # one launch for all fields (boatenv_env_state_host)
+            _lib.check(self._b._L.boatenv_env_state_host(self._b._h, 0, self._state), "boatenv_env_state_host")
+            self._fresh = True
+        return self._state[FIELDS[name]]
 
     s_x = property(lambda self: self._f("s_x"))
     s_y = property(lambda self: self._f("s_y"))
@@ -291,7 +300,7 @@ class _BoatFacade:
     v_y = property(lambda self: self._f("v_y"))
     v_r = property(lambda self: self._f("v_r"))
     rudder_angle = property(lambda self: self._f("rudder_angle"))
-    index = property(lambda self: int(self._b.get_field("index")[0].item()))
+    index = property(lambda self: int(self._f("index")))
 
     @property
     def t(self):
@@ -320,35 +329,33 @@ class BoatEnv:
         self.action_space = self._b.action_space
         self.observation_space = self._b.observation_space
         self.low_state, self.high_state = self.observation_space.low, self.observation_space.high
-        torch = _torch()
-        # pinned host buffers of the one-call-per-step host path (boatenv_step_host_term)
-        self._h_act = torch.zeros(1, dtype=self._b.dtype).pin_memory()
-        self._h_obs = torch.zeros((1, 11), dtype=self._b.dtype).pin_memory()
-        self._h_rew = torch.zeros(1, dtype=self._b.dtype).pin_memory()
-        self._h_done = torch.zeros(1, dtype=torch.uint8).pin_memory()
-        self._h_term = torch.zeros(1, dtype=torch.uint8).pin_memory()
+        # host buffers of the one-call-per-step host path (boatenv_step_host_term; zero-copy for one env)
+        ft = np.float32 if self._b.precision == 32 else np.float64
+        self._h_act, self._h_obs, self._h_rew = np.zeros(1, ft), np.zeros((1, 11), ft), np.zeros(1, ft)
+        self._h_done, self._h_term = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+        self._ptrs = tuple(x.ctypes.data for x in (self._h_act, self._h_obs, self._h_rew, self._h_done, self._h_term))
         self._b.reset()  # BoatEnv.__init__ builds a Boat (boat_env.py:15)
 
     def reset(self):
         obs = self._b.reset()
+        self.boat.invalidate()
         self.info["episode_reward"] = 0  # boat_env.py:122 (the other keys persist)
         self.state = obs[0].double().cpu().numpy()
         return self.state
 
     def step(self, action):
         self.action = action
-        self._h_act[0] = float(np.asarray(action).reshape(-1)[0])
+        self._h_act[0] = np.asarray(action).reshape(-1)[0]
         b = self._b
-        _lib.check(b._L.boatenv_step_host_term(b._h, self._h_act.data_ptr(), self._h_obs.data_ptr(),
-                                               self._h_rew.data_ptr(), self._h_done.data_ptr(),
-                                               self._h_term.data_ptr(), 0), "boatenv_step_host_term")
+        _lib.check(b._L.boatenv_step_host_term(b._h, *self._ptrs, 0), "boatenv_step_host_term")
+        self.boat.invalidate()
         code = int(self._h_term[0])
         self.reward = float(self._h_rew[0])
         if code:
             self.info["termination"] = TERM_NAMES[code]
             self.info[TERM_NAMES[code]] += 1
         self.info["episode_reward"] += self.reward
-        self.state = self._h_obs[0].double().numpy().copy()  # a fresh array every call, like boat_env.py:309
+        self.state = self._h_obs[0].astype(np.float64)  # a fresh array every call, like boat_env.py:309
         return self.state, self.reward, bool(self._h_done[0]), self.info
 
     def render(self):

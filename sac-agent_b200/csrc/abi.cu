@@ -43,7 +43,14 @@ struct boatenv_handle {
     cudaStream_t copy_in, compute, copy_out;
     cudaEvent_t ev_in[8], ev_k[8];
     bool host_path_ready;
+    // small-N zero-copy staging: one mapped pinned allocation the kernels read / write over PCIe directly
+    // (no copy engine, one launch + one synchronize per call): [act | obs | rew | done | term | 10 doubles]
+    char *zc_host, *zc_dev;
+    size_t zc_act, zc_obs, zc_rew, zc_done, zc_term, zc_fields;   // byte offsets
 };
+
+// envs up to which boatenv_step_host* runs zero-copy (beyond it the chunked copy-engine pipeline wins)
+constexpr long long kZeroCopyMaxEnvs = 2048;
 
 // ---------------------------------------------------------------------------------
 // Cardinal basis of the not-a-knot cubic spline through `fp` uniform knots (the curve
@@ -319,6 +326,7 @@ int boatenv_destroy(boatenv_t h) {
     cudaFree(h->h_rew);
     cudaFree(h->h_done);
     cudaFree(h->h_term);
+    if (h->zc_host) cudaFreeHost(h->zc_host);
     if (h->host_path_ready) {
         cudaStreamDestroy(h->copy_in);
         cudaStreamDestroy(h->compute);
@@ -421,6 +429,57 @@ static int ensure_host_path(boatenv_t h) {
 static int step_host_impl(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host, uint8_t *done_host,
                           uint8_t *term_host, uint32_t flags);
 
+static int ensure_zero_copy(boatenv_t h) {
+    if (h->zc_host) return BOATENV_OK;
+    const size_t n = (size_t)std::min<long long>(h->cfg.n_envs, kZeroCopyMaxEnvs), es = h->esize;
+    auto up = [](size_t x) { return (x + 127) / 128 * 128; };
+    h->zc_act = 0;
+    h->zc_obs = up(h->zc_act + n * es);
+    h->zc_rew = up(h->zc_obs + n * kObsDim * es);
+    h->zc_done = up(h->zc_rew + n * es);
+    h->zc_term = up(h->zc_done + n);
+    h->zc_fields = up(h->zc_term + n);
+    const size_t bytes = h->zc_fields + 16 * sizeof(double);
+    void *hp = nullptr, *dp = nullptr;
+    CUDA_TRY(cudaHostAlloc(&hp, bytes, cudaHostAllocMapped));
+    cudaError_t e = cudaHostGetDevicePointer(&dp, hp, 0);
+    if (e != cudaSuccess) { cudaFreeHost(hp); return (int)e; }
+    std::memset(hp, 0, bytes);
+    h->zc_host = (char *)hp;
+    h->zc_dev = (char *)dp;
+    return BOATENV_OK;
+}
+
+// Small-N step through host buffers: the kernel reads the actions from, and writes its outputs to, mapped
+// pinned memory; the caller's buffers (pinned or pageable) are filled by plain memcpy.
+static int step_host_zero_copy(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host,
+                               uint8_t *done_host, uint8_t *term_host, uint32_t flags) {
+    int rc = ensure_zero_copy(h);
+    if (rc) return rc;
+    const size_t n = (size_t)h->cfg.n_envs, es = h->esize;
+    std::memcpy(h->zc_host + h->zc_act, actions_host, n * es);
+    StepArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.env_begin = 0;
+    a.env_end = h->cfg.n_envs;
+    a.actions = h->zc_dev + h->zc_act;
+    a.ksteps = 1;
+    a.obs_out = h->zc_dev + h->zc_obs;
+    a.reward_out = h->zc_dev + h->zc_rew;
+    a.done_out = (uint8_t *)(h->zc_dev + h->zc_done);
+    a.term_out = (uint8_t *)(h->zc_dev + h->zc_term);
+    a.flags = flags;
+    a.reverse = (int)(h->launch_parity++ & 1u);
+    a.no_bulk = 1;
+    CUDA_TRY(h->precision == 32 ? launch_step_f32(h->cfg, a, h->compute) : launch_step_f64(h->cfg, a, h->compute));
+    CUDA_TRY(cudaStreamSynchronize(h->compute));
+    std::memcpy(obs_host, h->zc_host + h->zc_obs, n * kObsDim * es);
+    std::memcpy(reward_host, h->zc_host + h->zc_rew, n * es);
+    std::memcpy(done_host, h->zc_host + h->zc_done, n);
+    if (term_host) std::memcpy(term_host, h->zc_host + h->zc_term, n);
+    return BOATENV_OK;
+}
+
 int boatenv_step_host(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host, uint8_t *done_host,
                       uint32_t flags) {
     return step_host_impl(h, actions_host, obs_host, reward_host, done_host, nullptr, flags);
@@ -443,6 +502,7 @@ static int step_host_impl(boatenv_t h, const void *actions_host, void *obs_host,
     // caller has queued on this device (a reset / step on its stream) -- this call is blocking anyway.
     CUDA_TRY(cudaDeviceSynchronize());
     const long long n = h->cfg.n_envs;
+    if (n <= kZeroCopyMaxEnvs) return step_host_zero_copy(h, actions_host, obs_host, reward_host, done_host, term_host, flags);
     // chunks are multiples of the CTA tile so that every tile keeps its 16-byte alignment
     int nchunks = n >= 8LL * 65536 ? 8 : (n >= 4LL * 65536 ? 4 : 1);
     long long per = ((n + nchunks - 1) / nchunks + kTile - 1) / kTile * kTile;
@@ -495,6 +555,22 @@ int boatenv_set_field(boatenv_t h, int field, const void *in, void *stream) {
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(h->precision == 32 ? launch_set_field_f32(h->cfg, field, in, (cudaStream_t)stream)
                                 : launch_set_field_f64(h->cfg, field, in, (cudaStream_t)stream));
+    return BOATENV_OK;
+}
+
+int boatenv_env_state_host(boatenv_t h, int64_t env_index, double *out_host) {
+    if (!h || !out_host || env_index < 0 || env_index >= h->cfg.n_envs) return BOATENV_EINVAL;
+    if (!h->was_reset) return BOATENV_ESTATE;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = ensure_host_path(h);
+    if (!rc) rc = ensure_zero_copy(h);
+    if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());  // after whatever the caller queued on its own streams
+    double *dev = reinterpret_cast<double *>(h->zc_dev + h->zc_fields);
+    CUDA_TRY(h->precision == 32 ? launch_env_state_f32(h->cfg, env_index, dev, h->compute)
+                                : launch_env_state_f64(h->cfg, env_index, dev, h->compute));
+    CUDA_TRY(cudaStreamSynchronize(h->compute));
+    std::memcpy(out_host, h->zc_host + h->zc_fields, 10 * sizeof(double));
     return BOATENV_OK;
 }
 

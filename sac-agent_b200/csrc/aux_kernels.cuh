@@ -157,6 +157,18 @@ __global__ void boat_set_field_kernel(const __grid_constant__ DevCfg c, int fiel
     }
 }
 
+// All ten fields (boatenv_field order) of ONE env as doubles: what env.boat.* / return_all_data
+// (boat_env.py:128-140, main.py:94) read after a step.  One thread.
+template <typename T>
+__global__ void boat_env_state_kernel(const __grid_constant__ DevCfg c, long long i, double *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+#pragma unroll
+    for (int f = 0; f < D_COUNT; ++f) out[f] = (double)*dyn_scalar<T>(c, i, f);
+    const uint2 v = reinterpret_cast<const uint2 *>(block_section(c, i, c.off_idx))[i & 31];
+    out[BOATENV_F_STEP_INDEX] = (double)v.x;
+    out[BOATENV_F_EPISODE] = (double)v.y;
+}
+
 // counters[kCounterSlots][32 doubles, first 8 used] -> out[8]
 static __global__ void boat_reduce_counters_kernel(const double *counters, double *out) {
     const int t = threadIdx.x;

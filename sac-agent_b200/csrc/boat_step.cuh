@@ -787,7 +787,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
         const int rows = min(32, n_end - blk * 32);
         // ---- observations: the [rows][11] tile is contiguous in obs_out -> one bulk store ----
         T *gobs = reinterpret_cast<T *>(a.obs_out) + (size_t)blk * (32 * kObsDim);
-        if (rows == 32) {
+        if (rows == 32 && !a.no_bulk) {
             fence_proxy_async_smem();  // each lane: its st.shared rows -> visible to the async proxy
             __syncwarp();
 #ifndef BOAT_DEBUG_SKIP_OBS

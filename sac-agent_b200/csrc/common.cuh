@@ -103,6 +103,7 @@ struct StepArgs {
     const void *obs_in;        // previous observations (fused replay store only)
     uint32_t flags;
     int reverse;               // sweep direction of this launch (alternates, see boat_step.cuh)
+    int no_bulk;               // outputs live in mapped HOST memory (small-N zero-copy step): element-wise stores only
     // K > 1 launches: finished episodes are queued here (one region per CTA) and get their new wind
     // coefficients from a follow-up kernel at full occupancy (boat_setup_queue_kernel); null = inline
     uint2 *kq_entries;         // [regions][kq_cap] (env, new episode)

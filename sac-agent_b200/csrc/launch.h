@@ -19,6 +19,8 @@ cudaError_t launch_fill_actions_f32(const DevCfg &, unsigned long long step_coun
                                     cudaStream_t);
 cudaError_t launch_fill_actions_f64(const DevCfg &, unsigned long long step_counter, double scale, void *out,
                                     cudaStream_t);
+cudaError_t launch_env_state_f32(const DevCfg &, long long env, double *out, cudaStream_t);
+cudaError_t launch_env_state_f64(const DevCfg &, long long env, double *out, cudaStream_t);
 cudaError_t launch_wind_table(const DevCfg &, long long env, double *wv, double *wa, cudaStream_t);
 cudaError_t launch_reduce_counters(const double *counters, double *out, cudaStream_t);
 

@@ -102,6 +102,12 @@ cudaError_t FN(launch_set_field_)(const DevCfg &c, int field, const void *in, cu
     return cudaGetLastError();
 }
 
+cudaError_t FN(launch_env_state_)(const DevCfg &c, long long env, double *out, cudaStream_t st) {
+    boat_env_state_kernel<REAL><<<1, 32, 0, st>>>(c, env, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t FN(launch_fill_actions_)(const DevCfg &c, unsigned long long step_counter, double scale, void *out,
                                      cudaStream_t st) {
     const long long quads = (c.n_envs + (c.env_id_offset & 3) + 3) / 4;  // global quads touched by this shard

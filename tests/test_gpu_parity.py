@@ -385,19 +385,24 @@ def test_wind_tables_and_draws(S, O, experiment):
     env.close()
 
 
-def test_step_host_equals_step(S):
+@pytest.mark.parametrize("n,pinned", [
+    (300_000, True),   # > 4 * 65536: the chunked copy/compute overlap
+    (2048, True), (1000, False), (33, True), (1, False),  # <= 2048: the zero-copy path (mapped pinned staging)
+    (2049, False),     # smallest size of the copy-engine path, pageable buffers
+])
+def test_step_host_equals_step(S, n, pinned):
     import torch
     cfg = S.load_config(base_settings__experiment=6)
-    n = 300_000  # > 4 * 65536: exercises the chunked copy/compute overlap
-    a = make_env(S, cfg, n, "fp32", seed=2)
-    b = make_env(S, cfg, n, "fp32", seed=2)
+    a = make_env(S, cfg, n, "fp32", seed=2, auto_reset=True)
+    b = make_env(S, cfg, n, "fp32", seed=2, auto_reset=True)
     a.reset(); b.reset()
-    act_h = torch.empty(n, dtype=torch.float32).pin_memory()
-    obs_h = torch.empty((n, 11), dtype=torch.float32).pin_memory()
-    rew_h = torch.empty(n, dtype=torch.float32).pin_memory()
-    done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
-    for t in range(5):
-        acts = a.uniform_actions(t)
+    pin = (lambda x: x.pin_memory()) if pinned else (lambda x: x)
+    act_h = pin(torch.empty(n, dtype=torch.float32))
+    obs_h = pin(torch.empty((n, 11), dtype=torch.float32))
+    rew_h = pin(torch.empty(n, dtype=torch.float32))
+    done_h = pin(torch.empty(n, dtype=torch.uint8))
+    for t in range(12):
+        acts = a.uniform_actions(t, 4.0)  # big steps: resets inside the run
         act_h.copy_(acts)
         o, r, d, _ = a.step(acts)
         torch.cuda.synchronize()
