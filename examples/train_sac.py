@@ -44,6 +44,8 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--log-every", type=int, default=50)
     ap.add_argument("--no-graph", action="store_true", help="eager update / policy (for comparison)")
+    ap.add_argument("--overlap", action="store_true",
+                    help="acting and learning on two streams (OverlappedActorLearner: the policy lags one update)")
     args = ap.parse_args(argv)
 
     rank, local_rank, world = S.sharding.dist_info()
@@ -59,21 +61,29 @@ def main(argv=None):
                               use_cuda_graph=not args.no_graph, memory=mem)
     act = agent.choose_action if args.no_graph else agent.choose_action_graphed
     obs = env.reset()
+    pipe = S.OverlappedActorLearner(agent, env, done_flag_mode=1) if args.overlap else None
     losses = None
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for it in range(1, args.warmup_iters + args.iters + 1):
         if it == args.warmup_iters + 1:
+            if pipe:
+                pipe.finish()
             t0.record()
-        actions = act(obs).squeeze(-1)
-        agent.step_and_remember(env, actions, done_flag_mode=1)   # env.step + agent.remember, one kernel
-        for _ in range(args.updates_per_iter):
-            out = agent.learn()
-            losses = out if out is not None else losses
+        if pipe:
+            losses = pipe.step()
+        else:
+            actions = act(obs).squeeze(-1)
+            agent.step_and_remember(env, actions, done_flag_mode=1)   # env.step + agent.remember, one kernel
+            for _ in range(args.updates_per_iter):
+                out = agent.learn()
+                losses = out if out is not None else losses
         if rank == 0 and args.log_every and it % args.log_every == 0:
             c = env.counters()
             lv = [float(x) for x in losses] if losses is not None else [float("nan")] * 3
             print(f"iter {it:6d}  episodes {c['episodes']:.0f}  goals {c['reached_goal']:.0f}  "
                   f"losses v/pi/q {lv[0]:.3g} {lv[1]:.3g} {lv[2]:.3g}", flush=True)
+    if pipe:
+        pipe.finish()
     t1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
@@ -82,7 +92,7 @@ def main(argv=None):
     stats = S.all_reduce_counters(env.counters_tensor())
     sec = float(ms.item()) * 1e-3
     summary = {"example": "train_sac", "n_gpus": world, "envs_total": args.envs, "iters": args.iters,
-               "updates_per_iter": args.updates_per_iter, "cuda_graph": not args.no_graph,
+               "updates_per_iter": args.updates_per_iter, "cuda_graph": not args.no_graph, "overlap": bool(args.overlap),
                "env_steps_per_s": args.iters * args.envs / sec,
                "updates_per_s_per_replica": args.iters * args.updates_per_iter / sec,
                "ms_per_iter": 1e3 * sec / args.iters, "episodes": stats["episodes"],

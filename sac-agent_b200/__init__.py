@@ -18,11 +18,11 @@ from .sharding import all_reduce_counters, make_sharded_env, shard_range  # noqa
 __all__ = ["AttrDict", "load_config", "params_from_config", "BoatEnvError", "lib", "library_path",
            "BatchedBoatEnv", "BoatEnv", "Box", "TERM_NAMES", "ReplayBuffer", "ToyCar", "ToyParachute",
            "BatchedRecorder", "all_reduce_counters", "make_sharded_env", "shard_range",
-           "ContinuousAgent", "SACLearner"]
+           "ContinuousAgent", "SACLearner", "OverlappedActorLearner"]
 
 
 def __getattr__(name):  # the agent pulls in torch.nn / torch.optim: imported on first use only
-    if name in ("ContinuousAgent", "SACLearner"):
+    if name in ("ContinuousAgent", "SACLearner", "OverlappedActorLearner"):
         from . import continuous_agent
         return getattr(continuous_agent, name)
     raise AttributeError(name)

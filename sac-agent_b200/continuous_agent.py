@@ -23,6 +23,8 @@ the batch, initial weights and Gaussian draws of a recorded run of the reference
 """
 from __future__ import annotations
 
+import copy
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -143,6 +145,7 @@ class ContinuousAgent:
                        torch.zeros((B, O), **kw), torch.zeros(B, dtype=torch.uint8, device=self.device))
         self._eps = torch.zeros((2, B, A), **kw)  # the Gaussian draws of the two sample_normal calls of one update
         self._graph = None
+        self.capture_stream = None   # stream the update graph is captured on (None: torch's own capture stream)
         self._losses = None
         self._act_graphs = {}
         self.updates = 0
@@ -267,7 +270,7 @@ class ContinuousAgent:
                                     v.zero_() if saved_state[p] is None else v.copy_(saved_state[p][k])
         cur.wait_stream(side)
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(self._graph, stream=self.capture_stream):  # kernel nodes keep the capture stream's priority
             self._losses = self._update_static()
 
     def update_network_parameters(self, tau=None):
@@ -280,3 +283,86 @@ class ContinuousAgent:
     def load_models(self):
         for net in self.learner.networks():
             net.load_checkpoint()
+
+
+class OverlappedActorLearner:
+    """The loop of main.py:72-90 with acting and learning on two CUDA streams.
+
+    Sequentially, one iteration is policy (0.44 ms for 65536 envs) -> fused step + remember -> sample ->
+    update (0.84 ms), and the many small kernels of the update leave most of the GPU idle.  Here the env
+    stream runs policy(t + 1) and step(t + 1) while the learner stream runs update(t):
+
+        env stream     | policy(t)  step+store(t) | policy(t+1)  step+store(t+1) | ...
+        learner stream |            ............. | sample(t)  update(t)  publish | sample(t+1) ...
+
+    The policy reads one of two ACTING copies of the actor; update(t) publishes its weights into the copy
+    that policy(t + 2) reads, so acting lags the learner by one update (the reference's strictly
+    sequential loop is `ContinuousAgent.learn()` after every step; this class is the throughput mode).
+    Events order everything that shares memory: the ring rows of step t are complete before sample(t);
+    sample(t) has read the ring before step(t + 1) may overwrite its oldest rows; a copy is published
+    only after the policy launch that read it has finished, and read only after it was published.
+    """
+
+    def __init__(self, agent: ContinuousAgent, env, done_flag_mode=1):
+        self.agent, self.env, self.done_flag_mode = agent, env, int(done_flag_mode)
+        dev = agent.device
+        # the learner's small kernels go first whenever an SM frees up: without a priority they queue behind
+        # the thousand CTAs of each policy GEMM and the two streams do not overlap at all
+        self.s_env, self.s_learn = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)
+        if agent._graph is None:
+            agent.capture_stream = torch.cuda.Stream(dev, priority=-1)
+        self.acting = [copy.deepcopy(agent.actor).requires_grad_(False) for _ in range(2)]
+        ev = lambda: torch.cuda.Event()  # noqa: E731
+        self.ev_published, self.ev_policy = [ev(), ev()], [ev(), ev()]
+        self.ev_store, self.ev_sample = ev(), ev()
+        self._policy = [None, None]   # (graph, static action tensor) per acting copy
+        self.t = 0
+        self.losses = None
+        cur = torch.cuda.current_stream(dev)
+        self.s_env.wait_stream(cur)
+        self.s_learn.wait_stream(cur)
+
+    @torch.no_grad()
+    def _act(self, k):
+        obs = self.env.obs
+        if not self.agent.use_cuda_graph:
+            return self.acting[k].sample_normal(obs, reparameterize=False)[0]
+        if self._policy[k] is None:
+            for _ in range(2):
+                self.acting[k].sample_normal(obs, reparameterize=False)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.acting[k].sample_normal(obs, reparameterize=False)[0]
+            self._policy[k] = (g, out)
+        self._policy[k][0].replay()
+        return self._policy[k][1]
+
+    def step(self):
+        """One env step over all envs and (once the memory holds a batch) one update."""
+        a, k = self.agent, self.t & 1
+        with torch.cuda.stream(self.s_env):
+            self.s_env.wait_event(self.ev_published[k])     # update(t - 2) has been written into acting[k]
+            actions = self._act(k)
+            self.ev_policy[k].record(self.s_env)
+            self.s_env.wait_event(self.ev_sample)           # sample(t - 1) is done with the ring
+            a.step_and_remember(self.env, actions.squeeze(-1), done_flag_mode=self.done_flag_mode)
+            self.ev_store.record(self.s_env)
+        with torch.cuda.stream(self.s_learn):
+            self.s_learn.wait_event(self.ev_store)          # the rows of step t are complete
+            if a.memory.mem_cntr >= a.batch_size:
+                a.memory.sample_buffer(a.batch_size, as_torch=True, out=a._batch)
+                self.ev_sample.record(self.s_learn)
+                a._eps.normal_()
+                self.losses = a._run_update()
+                self.s_learn.wait_event(self.ev_policy[k])  # policy(t) has finished reading acting[k]
+                with torch.no_grad():
+                    torch._foreach_copy_(list(self.acting[k].parameters()), list(a.actor.parameters()))
+                self.ev_published[k].record(self.s_learn)
+        self.t += 1
+        return self.losses
+
+    def finish(self):
+        """Joins both streams into the caller's stream."""
+        cur = torch.cuda.current_stream(self.agent.device)
+        cur.wait_stream(self.s_env)
+        cur.wait_stream(self.s_learn)

@@ -166,3 +166,32 @@ def test_agent_api_on_batched_env():
         agent.learn()  # the captured graph still works on the reloaded (same-storage) parameters
     env.close()
     agent.memory.close()
+
+
+@pytest.mark.gpu
+def test_overlapped_actor_learner():
+    """Acting and learning on two streams: same env trajectory bookkeeping as the sequential loop (every
+    step stores n transitions, one update per step once a batch exists), finite losses, and the acting
+    copies hold exactly the actor weights the learner published (one or two updates old)."""
+    cfg = S.load_config(base_settings__experiment=6, agent__batch_size=512)
+    env = S.BatchedBoatEnv(cfg, 8192, seed=5, precision="fp32", device=0, auto_reset=True)
+    mem = S.ReplayBuffer(100_000, (11,), 1, precision="fp32", device=0, as_torch=True)   # wraps inside the run
+    agent = ContinuousAgent(cfg, None, (11,), env, device=0, seed=5, memory=mem)
+    env.reset()
+    pipe = S.OverlappedActorLearner(agent, env)
+    snaps = []
+    for it in range(40):
+        losses = pipe.step()
+        if it >= 37:
+            pipe.finish()
+            torch.cuda.synchronize()
+            snaps.append([p.detach().clone() for p in agent.actor.parameters()])
+    pipe.finish()
+    torch.cuda.synchronize()
+    assert agent.memory.mem_cntr == 40 * 8192 and agent.updates == 40
+    assert all(torch.isfinite(x).item() for x in losses)
+    # update(t) is published into acting[t & 1]: after step 39 acting[1] holds update 39, acting[0] update 38
+    assert all(torch.equal(p, q) for p, q in zip(pipe.acting[1].parameters(), snaps[2]))
+    assert all(torch.equal(p, q) for p, q in zip(pipe.acting[0].parameters(), snaps[1]))
+    assert float(env.counters()["episodes"]) >= 0
+    env.close(); mem.close()
