@@ -231,6 +231,40 @@ BOATENV_API int boatenv_step_store(boatenv_t h, boatreplay_t r, const void *acti
                        void *reward_out, uint8_t *done_out, uint8_t *term_out, int done_flag_mode,
                        uint32_t flags, void *stream);
 
+/* ---- the actor's tanh-squashed Gaussian head (networks/networks.py:47-70) ------------ */
+
+/* ActorNetwork.sample_normal after the two linear heads, fused: from mean, raw_std, eps (all
+ * float32 [rows][n_actions], device; eps = the standard-normal draw) and max_action float32
+ * [n_actions] to action [rows][n_actions] and log_prob [rows] (summed over the actions).
+ * backward: gradients w.r.t. mean and raw_std of the REPARAMETERISED draw (rsample, :61), given
+ * grad_action [rows][n_actions] and / or grad_log_prob [rows] (either may be NULL = zero). */
+BOATENV_API int boatagent_gaussian_head_forward(const float *mean, const float *raw_std, const float *eps,
+                                    const float *max_action, int64_t rows, int32_t n_actions,
+                                    float *action_out, float *log_prob_out, void *stream);
+BOATENV_API int boatagent_gaussian_head_backward(const float *mean, const float *raw_std, const float *eps,
+                                     const float *max_action, const float *grad_action,
+                                     const float *grad_log_prob, int64_t rows, int32_t n_actions,
+                                     float *grad_mean_out, float *grad_raw_std_out, void *stream);
+
+/* One optimiser step for ALL of the agent's networks -- torch.optim.Adam with its defaults
+ * (networks.py:31,88,121), a learning rate per slot -- and, for slots with a `target`, the Polyak
+ * average target = tau * param + (1 - tau) * target of update_network_parameters
+ * (continuous_agent.py:66-80), in one launch.  slots_host: HOST array (copied into the kernel
+ * arguments), all pointers float32 device tensors of `numel` elements.  state_dev: int64[2] on the
+ * device, zero-initialised by the caller: [0] = steps taken (incremented by the launch), [1] internal. */
+#define BOATAGENT_ADAM_MAX_SLOTS 64
+typedef struct boatagent_adam_slot {
+    float *param;
+    const float *grad;
+    float *exp_avg, *exp_avg_sq;
+    float *target;          /* NULL: no target network for this tensor */
+    int64_t numel;
+    float lr;
+    int32_t _pad;
+} boatagent_adam_slot;
+BOATENV_API int boatagent_adam_polyak_step(const boatagent_adam_slot *slots_host, int32_t n_slots, float beta1,
+                               float beta2, float eps, float tau, int64_t *state_dev, void *stream);
+
 /* ---- toy integrator envs (environment/toy_car.py, toy_parachute.py) ---------------- */
 
 typedef struct boattoy_handle *boattoy_t;

@@ -29,6 +29,7 @@ UNITS = {
     "abi.cu": [],
     "replay.cu": [],
     "toys.cu": ["-fmad=false"],
+    "agent_ops.cu": [],
 }
 
 

@@ -53,6 +53,9 @@ SIGNATURES = {
     "boatenv_get_counters": (C.c_int, [vp, C.POINTER(dbl), vp]),
     "boatenv_reduce_counters": (C.c_int, [vp, vp, vp]),
     "boatenv_fill_uniform_actions": (C.c_int, [vp, u64, dbl, vp, vp]),
+    "boatagent_gaussian_head_forward": (C.c_int, [vp, vp, vp, vp, i64, i32, vp, vp, vp]),
+    "boatagent_gaussian_head_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp]),
+    "boatagent_adam_polyak_step": (C.c_int, [vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]),
     "boatreplay_create": (C.c_int, [i64, i32, i32, C.c_int, C.c_int, C.POINTER(vp)]),
     "boatreplay_destroy": (C.c_int, [vp]),
     "boatreplay_store": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),

@@ -9,10 +9,10 @@ the data lives and how the update is driven:
 * the replay memory is libboatenv's device ring (buffer.py); `learn()` gathers its batch with the
   sample kernel straight into the learner's static input tensors -- no host round trip, no H2D
   copies (the reference does five per update, continuous_agent.py:103-107);
-* the update of one `learn()` is ONE CUDA-graph launch: the three forward/backward passes, the fused
-  Adam step and the Polyak update are captured once and replayed (about 150 small kernels
-  whose launch latency otherwise dominates a 1024 x 256 update); batch and Gaussian draws are static
-  inputs of the graph;
+* the update of one `learn()` is ONE CUDA-graph launch: the three forward/backward passes and one
+  fused Adam + Polyak kernel for all networks (`DeviceAdam`) are captured once and replayed (about a
+  hundred small kernels whose launch latency otherwise dominates a 1024 x 256 update); batch and
+  Gaussian draws are static inputs of the graph;
 * `choose_action` takes the [N, 11] observation tensor of a BatchedBoatEnv and returns [N, 1]
   actions without leaving the GPU (the reference syncs one action per env step through
   `.cpu().numpy()`, continuous_agent.py:61); a numpy observation of one env still works and
@@ -24,6 +24,7 @@ the batch, initial weights and Gaussian draws of a recorded run of the reference
 from __future__ import annotations
 
 import copy
+import ctypes as C
 
 import numpy as np
 import torch
@@ -33,11 +34,62 @@ from .buffer import ReplayBuffer
 from .networks import ActorNetwork, CriticNetwork, ValueNetwork
 
 
+class _AdamSlot(C.Structure):
+    """Mirror of `boatagent_adam_slot` (include/boatenv.h)."""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("target", C.c_void_p), ("numel", C.c_int64), ("lr", C.c_float), ("_pad", C.c_int32)]
+
+
+class DeviceAdam:
+    """torch.optim.Adam (default betas / eps, as networks.py:31,88,121 constructs it) for a list of
+    (parameters, learning rate) groups, fused with the Polyak average of the target network, as ONE
+    libboatenv launch per step (`boatagent_adam_polyak_step`, csrc/agent_ops.cu).  The moment tensors
+    and the step counter are ordinary torch tensors (`state_dict()` for checkpoints)."""
+
+    def __init__(self, groups, polyak=None, tau=0.0, betas=(0.9, 0.999), eps=1e-8):
+        from . import _lib
+        self._lib, self._L = _lib, _lib.lib()
+        self.params, lrs = [], []
+        for ps, lr in groups:
+            for p in ps:
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise ValueError("DeviceAdam: contiguous float32 CUDA parameters only")
+                self.params.append(p)
+                lrs.append(float(lr))
+        if len(self.params) > 64:
+            raise ValueError("DeviceAdam: at most 64 tensors (BOATAGENT_ADAM_MAX_SLOTS)")
+        self.exp_avg = [torch.zeros_like(p) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        self.state = torch.zeros(2, dtype=torch.int64, device=self.params[0].device)  # [steps taken, ticket]
+        self.betas, self.eps, self.tau = betas, float(eps), float(tau)
+        targets = {id(p): t for p, t in (polyak or [])}
+        self._slots = (_AdamSlot * len(self.params))()
+        for k, p in enumerate(self.params):
+            t = targets.get(id(p))
+            self._slots[k] = _AdamSlot(p.data_ptr(), 0, self.exp_avg[k].data_ptr(), self.exp_avg_sq[k].data_ptr(),
+                                       None if t is None else t.data_ptr(), p.numel(), lrs[k], 0)
+
+    def step(self, grads):
+        """grads: one contiguous float32 tensor per parameter, in construction order."""
+        for k, g in enumerate(grads):
+            self._slots[k].grad = g.data_ptr()
+        stream = torch.cuda.current_stream(self.params[0].device).cuda_stream
+        self._lib.check(self._L.boatagent_adam_polyak_step(self._slots, len(self.params), self.betas[0], self.betas[1],
+                                                           self.eps, self.tau, self.state.data_ptr(), stream),
+                        "boatagent_adam_polyak_step")
+
+    def state_tensors(self):
+        return [self.state] + self.exp_avg + self.exp_avg_sq
+
+    def state_dict(self):
+        return {"state": self.state, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+
+
 class SACLearner:
     """The five networks, their Adam optimisers and one SAC-v1 update (continuous_agent.py:96-154)."""
 
     def __init__(self, input_dims, n_actions, max_action, alpha, beta, gamma, tau, reward_scale, experiment_dir=None,
-                 device="cuda", capturable=False):
+                 device="cuda"):
         self.device = torch.device(device)
         self.gamma, self.tau, self.scale = float(gamma), float(tau), float(reward_scale)
         d = tuple(input_dims)
@@ -49,17 +101,20 @@ class SACLearner:
         self.target_value = ValueNetwork(experiment_dir, d, name="target_value_network")
         for net in self.networks():
             net.to(self.device)
-        on_gpu = self.device.type == "cuda"
-        kw = dict(capturable=capturable, fused=True) if on_gpu else {}
         # The reference keeps one Adam per network (networks.py:31,88,121) and steps them at three points of
         # learn().  Nothing computed after a step reads the stepped weights (the critics are stepped last, the
-        # value net is only read again by the Polyak update), so ONE Adam over two learning-rate groups,
-        # stepped once after the three backward passes, is the same arithmetic in two kernel launches.
+        # value net is only read again by the Polyak update), so ONE optimiser step over two learning rates
+        # after the three backward passes is the same arithmetic.  On the GPU that step and the Polyak
+        # average are one libboatenv launch (DeviceAdam); on the CPU (parity tests) it is torch.optim.Adam.
         self._actor_params = list(self.actor.parameters())
         self._critic_params = list(self.critic_1.parameters()) + list(self.critic_2.parameters())
         self._value_params = list(self.value.parameters())
-        self.optimizer = torch.optim.Adam([{"params": self._actor_params, "lr": alpha},
-                                           {"params": self._critic_params + self._value_params, "lr": beta}], **kw)
+        if self.device.type == "cuda":
+            self.optimizer = DeviceAdam([(self._actor_params, alpha), (self._critic_params + self._value_params, beta)],
+                                        polyak=list(zip(self._value_params, self.target_value.parameters())), tau=self.tau)
+        else:
+            self.optimizer = torch.optim.Adam([{"params": self._actor_params, "lr": alpha},
+                                               {"params": self._critic_params + self._value_params, "lr": beta}])
         for p in self.target_value.parameters():
             p.requires_grad_(False)
         self.update_network_parameters(tau=1.0)  # continuous_agent.py:55
@@ -109,8 +164,11 @@ class SACLearner:
 
         for p, g in zip(self._value_params + self._actor_params + self._critic_params, grads_v + grads_a + grads_c):
             p.grad = g
-        self.optimizer.step()
-        self.update_network_parameters()                                        # :154
+        if isinstance(self.optimizer, DeviceAdam):   # Adam for all four networks + update_network_parameters (:154)
+            self.optimizer.step(grads_a + grads_c + grads_v)
+        else:
+            self.optimizer.step()
+            self.update_network_parameters()                                    # :154
         return value_loss.detach(), actor_loss.detach(), critic_loss.detach()
 
 
@@ -133,7 +191,7 @@ class ContinuousAgent:
             as_torch=True)
         self.learner = SACLearner(self.input_dims, self.get_n_actions(), self.get_max_actions(), a.learning_rate_alpha,
                                   a.learning_rate_beta, a.gamma, a.tvn_parameter_modulation_tau, a.reward_scale,
-                                  experiment_dir=experiment_dir, device=self.device, capturable=bool(use_cuda_graph))
+                                  experiment_dir=experiment_dir, device=self.device)
         L = self.learner
         self.actor, self.critic_1, self.critic_2 = L.actor, L.critic_1, L.critic_2
         self.value, self.target_value = L.value, L.target_value
@@ -245,15 +303,10 @@ class ContinuousAgent:
         stream; weights and optimiser state are then put back, i.e. every `learn()` -- the first one
         included -- is exactly one update."""
         L = self.learner
-        opts = (L.optimizer,)
         params = [p for net in L.networks() for p in net.parameters()]
+        opt_state = L.optimizer.state_tensors()   # Adam moments + step counter (fresh or carried over from eager updates)
         saved_params = [p.detach().clone() for p in params]
-        saved_state = {}
-        for opt in opts:
-            for group in opt.param_groups:
-                for p in group["params"]:
-                    st = opt.state.get(p)
-                    saved_state[p] = None if not st else {k: v.clone() for k, v in st.items() if torch.is_tensor(v)}
+        saved_state = [t.clone() for t in opt_state]
         cur = torch.cuda.current_stream(self.device)
         side = torch.cuda.Stream(self.device)
         side.wait_stream(cur)
@@ -262,12 +315,7 @@ class ContinuousAgent:
                 self._update_static()
             with torch.no_grad():
                 torch._foreach_copy_(params, saved_params)
-                for opt in opts:
-                    for group in opt.param_groups:
-                        for p in group["params"]:
-                            for k, v in opt.state[p].items():
-                                if torch.is_tensor(v):
-                                    v.zero_() if saved_state[p] is None else v.copy_(saved_state[p][k])
+                torch._foreach_copy_(opt_state, saved_state)
         cur.wait_stream(side)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph, stream=self.capture_stream):  # kernel nodes keep the capture stream's priority

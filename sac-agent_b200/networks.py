@@ -2,9 +2,10 @@
 batched over envs.  Layer names, shapes and the order they are created in are the reference's
 (`fc1, fc2, mean, std` / `fc1, fc2, q` / `fc1, fc2, v`, all 256 wide), so a `state_dict` saved by the
 reference's `BaseNetwork.save_checkpoint` (networks/base_network.py:13-17) loads here unchanged and
-vice versa.  Plain dense layers: cuBLAS is the right tool for them, there is no custom kernel here;
-the B200-specific part of the learner is how it is driven (continuous_agent.py: one CUDA graph per
-update, batch gathered on the device by libboatenv's replay kernels).
+vice versa.  The dense layers are cuBLAS; the element-wise tail of the policy (tanh-squashed Gaussian
+draw and its log-probability: ~60 tiny launches forward + backward in PyTorch) is one libboatenv kernel
+each way on the GPU (csrc/agent_ops.cu).  How the learner is driven is in continuous_agent.py (one CUDA
+graph per update, batch gathered on the device by libboatenv's replay kernels).
 """
 from __future__ import annotations
 
@@ -18,6 +19,44 @@ import torch.nn.functional as F
 LOG_STD_MAX, LOG_STD_MIN = 2.0, -5.0   # networks.py:48-49
 REPARAM_NOISE = 1e-6                   # networks.py:22
 _HALF_LOG_2PI = 0.5 * math.log(2.0 * math.pi)
+
+
+class _FusedGaussianHead(torch.autograd.Function):
+    """sample_normal after the linear heads as one libboatenv kernel forward and one backward
+    (csrc/agent_ops.cu).  Backward is that of the reparameterised draw."""
+
+    @staticmethod
+    def forward(ctx, mean, raw_std, eps, max_action):
+        from . import _lib
+        L = _lib.lib()
+        mean, raw_std, eps = mean.contiguous(), raw_std.contiguous(), eps.contiguous()
+        rows, n_actions = mean.shape
+        action = torch.empty_like(mean)
+        log_prob = torch.empty((rows, 1), dtype=mean.dtype, device=mean.device)
+        stream = torch.cuda.current_stream(mean.device).cuda_stream
+        _lib.check(L.boatagent_gaussian_head_forward(mean.data_ptr(), raw_std.data_ptr(), eps.data_ptr(),
+                                                     max_action.data_ptr(), rows, n_actions, action.data_ptr(),
+                                                     log_prob.data_ptr(), stream), "boatagent_gaussian_head_forward")
+        ctx.save_for_backward(mean, raw_std, eps, max_action)
+        ctx.set_materialize_grads(False)
+        return action, log_prob
+
+    @staticmethod
+    def backward(ctx, grad_action, grad_log_prob):
+        from . import _lib
+        L = _lib.lib()
+        mean, raw_std, eps, max_action = ctx.saved_tensors
+        rows, n_actions = mean.shape
+        ga = None if grad_action is None else grad_action.contiguous()
+        gl = None if grad_log_prob is None else grad_log_prob.contiguous()
+        grad_mean, grad_raw = torch.empty_like(mean), torch.empty_like(mean)
+        stream = torch.cuda.current_stream(mean.device).cuda_stream
+        _lib.check(L.boatagent_gaussian_head_backward(mean.data_ptr(), raw_std.data_ptr(), eps.data_ptr(),
+                                                      max_action.data_ptr(), None if ga is None else ga.data_ptr(),
+                                                      None if gl is None else gl.data_ptr(), rows, n_actions,
+                                                      grad_mean.data_ptr(), grad_raw.data_ptr(), stream),
+                   "boatagent_gaussian_head_backward")
+        return grad_mean, grad_raw, None, None
 
 
 class BaseNetwork(nn.Module):
@@ -61,10 +100,16 @@ class ActorNetwork(BaseNetwork):
         """networks.py:47-70.  `eps` (standard-normal, shape [B, n_actions]) replaces the draw -- the
         parity tests inject the reference's noise through it."""
         mean, std = self.forward(state)
-        log_std = LOG_STD_MIN + 0.5 * (LOG_STD_MAX - LOG_STD_MIN) * (torch.tanh(std) + 1.0)
-        std = log_std.exp()
         if eps is None:
             eps = torch.randn_like(mean)
+        if mean.is_cuda and mean.dtype == torch.float32 and (reparameterize or not torch.is_grad_enabled()):
+            # on the GPU the whole head is one kernel (and one for its backward); a non-reparameterised
+            # draw is only fused where no gradient is wanted, which is how the update and acting use it
+            if not reparameterize:
+                mean, std = mean.detach(), std.detach()
+            return _FusedGaussianHead.apply(mean, std, eps.to(mean.dtype), self.max_action)
+        log_std = LOG_STD_MIN + 0.5 * (LOG_STD_MAX - LOG_STD_MIN) * (torch.tanh(std) + 1.0)
+        std = log_std.exp()
         if reparameterize:
             u = mean + eps * std              # Normal.rsample
         else:

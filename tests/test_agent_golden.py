@@ -25,11 +25,11 @@ from sac_agent_b200.continuous_agent import ContinuousAgent, SACLearner  # noqa:
 GOLDEN = os.path.join(ROOT, "tests", "golden", "agent_update.npz")
 
 
-def _learner(meta, device, capturable=False):
+def _learner(meta, device):
     L = SACLearner((11,), 1, np.array([1.0], dtype=np.float32), float(meta["meta/learning_rate_alpha"]),
                    float(meta["meta/learning_rate_beta"]), float(meta["meta/gamma"]),
                    float(meta["meta/tvn_parameter_modulation_tau"]), float(meta["meta/reward_scale"]),
-                   device=device, capturable=capturable)
+                   device=device)
     return L
 
 
@@ -195,3 +195,76 @@ def test_overlapped_actor_learner():
     assert all(torch.equal(p, q) for p, q in zip(pipe.acting[0].parameters(), snaps[1]))
     assert float(env.counters()["episodes"]) >= 0
     env.close(); mem.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_actions", [1, 3])
+def test_fused_gaussian_head_matches_the_torch_expression(n_actions):
+    """csrc/agent_ops.cu (one kernel forward, one backward) against the element-wise PyTorch expression of
+    networks.py:47-70 evaluated in float64 on the same inputs: values and both gradients."""
+    from sac_agent_b200.networks import ActorNetwork
+    torch.manual_seed(0)
+    B = 1500
+    mean = (torch.randn(B, n_actions, device="cuda") * 1.5)
+    raw = torch.randn(B, n_actions, device="cuda") * 2.0
+    eps = torch.randn(B, n_actions, device="cuda")
+    ga, gl = torch.randn(B, n_actions, device="cuda"), torch.randn(B, 1, device="cuda")
+    max_a = np.linspace(1.0, 0.5, n_actions).astype(np.float32)  # <= 1: the formula takes log(1 - action^2 + 1e-6)
+
+    class Head(ActorNetwork):  # the two linear heads replaced by leaf tensors
+        def forward(self, state):
+            return self._m, self._r
+
+    def run(dtype):
+        net = Head(None, (11,), max_a, n_actions=n_actions).cuda().to(dtype)
+        net._m = mean.to(dtype).clone().requires_grad_(True)
+        net._r = raw.to(dtype).clone().requires_grad_(True)
+        act, lp = net.sample_normal(None, reparameterize=True, eps=eps.to(dtype))
+        (act * ga.to(dtype)).sum().add((lp * gl.to(dtype)).sum()).backward()
+        with torch.no_grad():
+            act0, lp0 = net.sample_normal(None, reparameterize=False, eps=eps.to(dtype))
+        assert torch.equal(act0, act.detach()) and torch.equal(lp0, lp.detach())
+        return [x.detach().double() for x in (act, lp, net._m.grad, net._r.grad)]
+
+    fused, ref = run(torch.float32), run(torch.float64)
+    # log(1 - action^2 + 1e-6) cancels catastrophically in float32 once tanh saturates (the reference has the
+    # same property): rows with |u| > 3 in any action are compared on the action only
+    sd = torch.exp(-5.0 + 3.5 * (torch.tanh(raw.double()) + 1.0))
+    ok = ((mean.double() + eps.double() * sd).abs() <= 3.0).all(dim=1)
+    assert ok.float().mean().item() > 0.4
+    for name, a, b in zip(("action", "log_prob", "grad_mean", "grad_raw_std"), fused, ref):
+        if name != "action":
+            a, b = a[ok], b[ok]
+        err = ((a - b).abs() / b.abs().clamp_min(1.0)).max().item()
+        assert err < 2e-4, (name, err)
+
+
+@pytest.mark.gpu
+def test_device_adam_matches_torch_adam_and_polyak():
+    """One libboatenv launch (Adam for every tensor + Polyak average of the marked ones) against
+    torch.optim.Adam + the reference's tau * value + (1 - tau) * target, 25 steps, two learning rates."""
+    from sac_agent_b200.continuous_agent import DeviceAdam
+    torch.manual_seed(1)
+    shapes = [(256, 11), (256,), (256, 256), (1, 256), (1,), (5000,)]
+    ref = [torch.randn(s, device="cuda").requires_grad_(True) for s in shapes]
+    ours = [p.detach().clone() for p in ref]
+    tgt_ref = [torch.randn_like(p) for p in ref[:2]]
+    tgt_ours = [t.clone() for t in tgt_ref]
+    lrs = [5e-3, 5e-3, 3e-4, 3e-4, 3e-4, 3e-4]
+    opt_ref = torch.optim.Adam([{"params": ref[:2], "lr": 5e-3}, {"params": ref[2:], "lr": 3e-4}])
+    opt = DeviceAdam([(ours[:2], 5e-3), (ours[2:], 3e-4)], polyak=list(zip(ours[:2], tgt_ours)), tau=0.005)
+    for step in range(25):
+        grads = [torch.randn_like(p) * (10.0 ** ((step % 5) - 3)) for p in ref]
+        for p, g in zip(ref, grads):
+            p.grad = g.clone()
+        opt_ref.step()
+        with torch.no_grad():
+            for p, t in zip(ref[:2], tgt_ref):
+                t.copy_(0.005 * p + (1 - 0.005) * t)
+        opt.step(grads)
+    torch.cuda.synchronize()
+    assert int(opt.state[0]) == 25 and int(opt.state[1]) == 0
+    for p, q, lr in zip(ref, ours, lrs):
+        assert (p.detach() - q).abs().max().item() <= 1e-6 + 1e-3 * lr * 25
+    for t, u in zip(tgt_ref, tgt_ours):
+        assert (t - u).abs().max().item() <= 1e-5
