@@ -73,10 +73,12 @@ class DeviceAdam:
         """grads: one contiguous float32 tensor per parameter, in construction order."""
         for k, g in enumerate(grads):
             self._slots[k].grad = g.data_ptr()
-        stream = torch.cuda.current_stream(self.params[0].device).cuda_stream
-        self._lib.check(self._L.boatagent_adam_polyak_step(self._slots, len(self.params), self.betas[0], self.betas[1],
-                                                           self.eps, self.tau, self.state.data_ptr(), stream),
-                        "boatagent_adam_polyak_step")
+        with torch.cuda.device(self.params[0].device):  # the ABI launches on the current device
+            stream = torch.cuda.current_stream().cuda_stream
+            self._lib.check(self._L.boatagent_adam_polyak_step(self._slots, len(self.params), self.betas[0],
+                                                               self.betas[1], self.eps, self.tau,
+                                                               self.state.data_ptr(), stream),
+                            "boatagent_adam_polyak_step")
 
     def state_tensors(self):
         return [self.state] + self.exp_avg + self.exp_avg_sq

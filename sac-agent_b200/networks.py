@@ -33,10 +33,11 @@ class _FusedGaussianHead(torch.autograd.Function):
         rows, n_actions = mean.shape
         action = torch.empty_like(mean)
         log_prob = torch.empty((rows, 1), dtype=mean.dtype, device=mean.device)
-        stream = torch.cuda.current_stream(mean.device).cuda_stream
-        _lib.check(L.boatagent_gaussian_head_forward(mean.data_ptr(), raw_std.data_ptr(), eps.data_ptr(),
-                                                     max_action.data_ptr(), rows, n_actions, action.data_ptr(),
-                                                     log_prob.data_ptr(), stream), "boatagent_gaussian_head_forward")
+        with torch.cuda.device(mean.device):  # the ABI launches on the current device
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.boatagent_gaussian_head_forward(mean.data_ptr(), raw_std.data_ptr(), eps.data_ptr(),
+                                                         max_action.data_ptr(), rows, n_actions, action.data_ptr(),
+                                                         log_prob.data_ptr(), stream), "boatagent_gaussian_head_forward")
         ctx.save_for_backward(mean, raw_std, eps, max_action)
         ctx.set_materialize_grads(False)
         return action, log_prob
@@ -50,12 +51,13 @@ class _FusedGaussianHead(torch.autograd.Function):
         ga = None if grad_action is None else grad_action.contiguous()
         gl = None if grad_log_prob is None else grad_log_prob.contiguous()
         grad_mean, grad_raw = torch.empty_like(mean), torch.empty_like(mean)
-        stream = torch.cuda.current_stream(mean.device).cuda_stream
-        _lib.check(L.boatagent_gaussian_head_backward(mean.data_ptr(), raw_std.data_ptr(), eps.data_ptr(),
-                                                      max_action.data_ptr(), None if ga is None else ga.data_ptr(),
-                                                      None if gl is None else gl.data_ptr(), rows, n_actions,
-                                                      grad_mean.data_ptr(), grad_raw.data_ptr(), stream),
-                   "boatagent_gaussian_head_backward")
+        with torch.cuda.device(mean.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.boatagent_gaussian_head_backward(mean.data_ptr(), raw_std.data_ptr(), eps.data_ptr(),
+                                                          max_action.data_ptr(), None if ga is None else ga.data_ptr(),
+                                                          None if gl is None else gl.data_ptr(), rows, n_actions,
+                                                          grad_mean.data_ptr(), grad_raw.data_ptr(), stream),
+                       "boatagent_gaussian_head_backward")
         return grad_mean, grad_raw, None, None
 
 
