@@ -15,6 +15,8 @@ recorded run of the reference's own learn() in tests/test_agent_golden.py.
 
     python examples/train_sac.py --envs 65536 --iters 200
     torchrun --nproc-per-node 8 examples/train_sac.py --envs 65536        # replicas: one agent per GPU shard
+    torchrun --nproc-per-node 8 examples/train_sac.py --experiments-root experiments --tune
+                                          # the reference's `main.py -p 8`: a tuned_configs.yaml draw per member
 
 Multi-GPU is "replicas only" (SURVEY.md 8e): every rank trains its own agent on its own env shard,
 like the reference's `-p` mode runs independent models; only the episode statistics are all-reduced.
@@ -44,6 +46,11 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--log-every", type=int, default=50)
     ap.add_argument("--no-graph", action="store_true", help="eager update / policy (for comparison)")
+    ap.add_argument("--experiments-root", default=None,
+                    help="write the reference's experiment tree (configs/, checkpoints/, console.csv, overview.csv, "
+                         "terminations.csv; main.py:116-133) under this directory, one experiment per rank")
+    ap.add_argument("--tune", action="store_true",
+                    help="population mode (main.py -p): every rank trains with its own tuned_configs.yaml draw")
     ap.add_argument("--overlap", action="store_true",
                     help="acting and learning on two streams (OverlappedActorLearner: the policy lags one update)")
     args = ap.parse_args(argv)
@@ -54,15 +61,25 @@ def main(argv=None):
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.manual_seed(args.seed + rank)
     cfg = S.load_config(base_settings__experiment=args.experiment)
+    exp = None
+    if args.experiments_root:   # utils/build_experiment.py: one experiment directory per population member
+        import random
+        exp = S.Experiment(experiment_name=f"experiment_r{rank}", subdir=f"setting_{args.experiment}",
+                           root=args.experiments_root, rng=random.Random(args.seed + rank))
+        tuned = exp.save_configs(cfg)
+        if args.tune:
+            cfg = tuned
     env = S.make_sharded_env(cfg, args.envs, seed=args.seed, precision="fp32", auto_reset=True)
     mem = S.ReplayBuffer(max(args.buffer, env.n_envs), (11,), 1, precision="fp32", device=local_rank,
                          seed=args.seed + rank, as_torch=True)
-    agent = S.ContinuousAgent(cfg, None, env.observation_space.shape, env, device=local_rank, seed=args.seed + rank,
+    agent = S.ContinuousAgent(cfg, exp.experiment_dir if exp else None, env.observation_space.shape, env,
+                              device=local_rank, seed=args.seed + rank,
                               use_cuda_graph=not args.no_graph, memory=mem)
     act = agent.choose_action if args.no_graph else agent.choose_action_graphed
     obs = env.reset()
     pipe = S.OverlappedActorLearner(agent, env, done_flag_mode=1) if args.overlap else None
     losses = None
+    rows, best, prev = [], float("-inf"), {"episodes": 0.0, "return_sum": 0.0}
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for it in range(1, args.warmup_iters + args.iters + 1):
         if it == args.warmup_iters + 1:
@@ -77,6 +94,18 @@ def main(argv=None):
             for _ in range(args.updates_per_iter):
                 out = agent.learn()
                 losses = out if out is not None else losses
+        if exp and args.log_every and it % args.log_every == 0:
+            # one console.csv row per logging interval: the mean return of the episodes that ended in it
+            c = env.counters()
+            n = c["episodes"] - prev["episodes"]
+            score = (c["return_sum"] - prev["return_sum"]) / n if n else float("nan")
+            prev = c
+            if n and score > best:
+                best = score
+                agent.save_models()          # main.py:104-106 keeps the checkpoints of improving episodes
+            kind = max(S.TERM_NAMES[1:], key=lambda k: c[k])
+            avg = c["return_sum"] / c["episodes"] if c["episodes"] else float("nan")
+            rows.append([(rank, it), f"{kind}-{int(c[kind])}", score, best, avg, "", ""])
         if rank == 0 and args.log_every and it % args.log_every == 0:
             c = env.counters()
             lv = [float(x) for x in losses] if losses is not None else [float("nan")] * 3
@@ -98,6 +127,18 @@ def main(argv=None):
                "ms_per_iter": 1e3 * sec / args.iters, "episodes": stats["episodes"],
                "mean_return": stats["return_mean"], "reached_goal": stats["reached_goal"],
                "losses_v_pi_q": [float(x) for x in losses] if losses is not None else None}
+    if exp:
+        c = env.counters()
+        exp.write_console(rows)
+        exp.append_overview(best)
+        exp.write_terminations(S.info_from_counters(c, max(S.TERM_NAMES[1:], key=lambda k: c[k])))
+        summary["experiment_dir"], summary["best_interval_return"] = exp.experiment_dir, best
+        if args.tune:
+            summary["hpset"] = exp.tuner.hpset
+        if world > 1:   # the population's best member, like reading overview.csv after a `-p` run
+            scores = [None] * world
+            torch.distributed.all_gather_object(scores, (best, rank, exp.experiment_name))
+            summary["population_best"] = max(scores)
     if rank == 0:
         print(json.dumps(summary), flush=True)
     env.close(); mem.close()

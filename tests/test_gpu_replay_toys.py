@@ -218,3 +218,27 @@ def test_end_to_end_sac_loop_smoke(S):
     out = mod.main(["--envs", "4096", "--iters", "30", "--warmup-iters", "5", "--buffer", "65536", "--log-every", "30"])
     assert all(math.isfinite(x) for x in out["losses_v_pi_q"])
     assert out["env_steps_per_s"] > 0 and out["cuda_graph"]
+
+
+def test_sac_example_writes_the_reference_experiment_tree(S, tmp_path):
+    """a run leaves configs/, checkpoints/, console.csv, terminations.csv and an
+    overview.csv line behind (main.py:116-133), trained with its tuned_configs.yaml draw."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "train_sac.py")
+    spec = importlib.util.spec_from_file_location("train_sac", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.main(["--envs", "4096", "--iters", "40", "--warmup-iters", "0", "--buffer", "65536", "--log-every", "10",
+                    "--experiment", "6", "--experiments-root", str(tmp_path), "--tune", "--overlap"])
+    d = out["experiment_dir"]
+    assert os.path.dirname(d) == os.path.join(str(tmp_path), "setting_6")
+    tuned = S.get_experiment_config(d)
+    assert tuned.agent.learning_rate_alpha == out["hpset"]["alpha"] and tuned.base_settings.experiment == 6
+    for f in ("console.csv", "terminations.csv", "configs/original_config.yaml", "configs/tuned_configs.yaml"):
+        assert os.path.isfile(os.path.join(d, f)), f
+    assert len(open(os.path.join(d, "console.csv")).read().splitlines()) == 1 + 4
+    assert os.path.isfile(os.path.join(os.path.dirname(d), "overview.csv"))
+    if out["best_interval_return"] > float("-inf"):   # a checkpoint was saved for the best interval
+        assert sorted(os.listdir(os.path.join(d, "checkpoints"))) == sorted(
+            ["actor_network", "critic_network_1", "critic_network_2", "value_network", "target_value_network"])
