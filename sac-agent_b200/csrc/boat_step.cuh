@@ -295,9 +295,13 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 #ifndef BOAT_STAGES
 #define BOAT_STAGES 1         // state blocks in flight per warp beyond the one being computed (TMA pipeline depth)
 #endif
-template <typename T> struct StepTuning;
-template <> struct StepTuning<float> { static constexpr int kMinBlocks = BOAT_MINBLOCKS_F32; };
-template <> struct StepTuning<double> { static constexpr int kMinBlocks = 1; };
+#ifndef BOAT_MINBLOCKS_F64
+#define BOAT_MINBLOCKS_F64 3  // the same for the K = 1 fp64 validation kernels: they are latency bound (dependent
+#endif                        // DFMA chains), 3 CTAs per SM at 56-80 registers beat 1 CTA at 134 by 7-24 %
+template <typename T, bool KMULTI> struct StepTuning;
+template <bool KMULTI> struct StepTuning<float, KMULTI> { static constexpr int kMinBlocks = BOAT_MINBLOCKS_F32; };
+template <> struct StepTuning<double, false> { static constexpr int kMinBlocks = BOAT_MINBLOCKS_F64; };
+template <> struct StepTuning<double, true> { static constexpr int kMinBlocks = 1; };  // 230 registers live across the K loop
 constexpr int kStages = BOAT_STAGES;
 
 #ifndef BOAT_SETUP_WARPS
@@ -394,7 +398,7 @@ struct CtaSmem {
 // written back right after the sub-step and the (rare) slow path patches the affected envs
 // in global memory, so that almost nothing is live in registers across the slow path.
 template <typename T, int WK, bool KMULTI>
-__global__ void __launch_bounds__(kTile + 32 * setup_warps<WK, KMULTI>(), StepTuning<T>::kMinBlocks)
+__global__ void __launch_bounds__(kTile + 32 * setup_warps<WK, KMULTI>(), StepTuning<T, KMULTI>::kMinBlocks)
 boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool kCurves = (WK == WIND_VEL_CURVE || WK == WIND_ANGLE_RECT || WK == WIND_BOTH);
