@@ -96,6 +96,11 @@ def main():
         boat_case("exp6_fp32_16M_k8_long_episodes", 6, "fp32", 16 * M, 0.02, 4 + 5 + (112 + 44) / 8, 30, 30, k=8)
         boat_case("exp6_fp32_16M_k1_long_episodes", 6, "fp32", 16 * M, 0.02, 165, 100, 100)
         return
+    if os.environ.get("BENCH_EXTRA_ONLY") == "fp32":
+        boat_case("exp1_fp32_16M", 1, "fp32", 16 * M, 1.0, 133, 300, 100)
+        boat_case("exp4_fp32_16M", 4, "fp32", 16 * M, 1.0, 149, 300, 100)
+        boat_case("exp6_fp32_16M", 6, "fp32", 16 * M, 1.0, 165, 600, 100)
+        return
     if os.environ.get("BENCH_EXTRA_ONLY") == "fp64":
         boat_case("exp3_fp64_4M", 3, "fp64", 4 * M, 0.05, 249, 50, 50)
         boat_case("exp6_fp64_4M", 6, "fp64", 4 * M, 1.0, 8 + 104 + 104 + 88 + 8 + 1, 300, 50)
