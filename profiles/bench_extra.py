@@ -96,6 +96,9 @@ def main():
         boat_case("exp6_fp32_16M_k8_long_episodes", 6, "fp32", 16 * M, 0.02, 4 + 5 + (112 + 44) / 8, 30, 30, k=8)
         boat_case("exp6_fp32_16M_k1_long_episodes", 6, "fp32", 16 * M, 0.02, 165, 100, 100)
         return
+    if os.environ.get("BENCH_EXTRA_ONLY") == "reset":
+        reset_cases(M)
+        return
     if os.environ.get("BENCH_EXTRA_ONLY") == "fp32":
         boat_case("exp1_fp32_16M", 1, "fp32", 16 * M, 1.0, 133, 300, 100)
         boat_case("exp4_fp32_16M", 4, "fp32", 16 * M, 1.0, 149, 300, 100)
@@ -124,6 +127,7 @@ def main():
     boat_case("exp6_fp32_16M_k8_long_episodes", 6, "fp32", 16 * M, 0.02, 4 + 5 + (112 + 44) / 8, 30, 30, k=8)
     boat_case("exp6_fp32_16M_k1_long_episodes", 6, "fp32", 16 * M, 0.02, 165, 100, 100)
 
+    reset_cases(M)
     replay_cases(M)
 
     # toy envs, 1M envs each, fp32 (BASELINE.json configs[3]): k iterations per launch
@@ -134,6 +138,21 @@ def main():
     ms = timed(lambda: (chute.reset(), chute.step(100)), 20)
     emit("toy_parachute_1M_k100", ms, M * 100, "env-iterations")
     car.close(); chute.close()
+
+
+def reset_cases(M):
+    """BoatEnv.reset (boat_env.py:120-126, a new Boat + a new Wind per env; 2.2 ms per env in the reference):
+    the explicit reset of a whole population -- one warp-cooperative wind setup per env -- and a masked one."""
+    for exp, n in ((1, 16 * M), (6, 16 * M)):
+        cfg = S.load_config(base_settings__experiment=exp)
+        env = S.BatchedBoatEnv(cfg, n, seed=1, precision="fp32", device=0, auto_reset=True)
+        ms = timed(lambda: env.reset(), 5, warmup=1)
+        emit(f"reset_exp{exp}_fp32_16M", ms, n, "env-resets")
+        if exp == 6:
+            mask = (torch.arange(n, device="cuda") % 300 == 0).to(torch.uint8)   # the steady-state reset share of one step
+            ms = timed(lambda: env.reset(mask), 10, warmup=2)
+            emit("reset_exp6_fp32_16M_masked_1_in_300", ms, int(mask.sum().item()), "env-resets")
+        env.close()
 
 
 def replay_cases(M):
