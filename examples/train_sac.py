@@ -51,6 +51,8 @@ def main(argv=None):
                          "terminations.csv; main.py:116-133) under this directory, one experiment per rank")
     ap.add_argument("--tune", action="store_true",
                     help="population mode (main.py -p): every rank trains with its own tuned_configs.yaml draw")
+    ap.add_argument("--policy-precision", default="fp32", choices=["fp32", "tf32", "bf16"],
+                    help="dense layers of choose_action on tensor-core inputs (acting only; the learner stays fp32)")
     ap.add_argument("--overlap", action="store_true",
                     help="acting and learning on two streams (OverlappedActorLearner: the policy lags one update)")
     args = ap.parse_args(argv)
@@ -74,7 +76,7 @@ def main(argv=None):
                          seed=args.seed + rank, as_torch=True)
     agent = S.ContinuousAgent(cfg, exp.experiment_dir if exp else None, env.observation_space.shape, env,
                               device=local_rank, seed=args.seed + rank,
-                              use_cuda_graph=not args.no_graph, memory=mem)
+                              use_cuda_graph=not args.no_graph, memory=mem, policy_precision=args.policy_precision)
     act = agent.choose_action if args.no_graph else agent.choose_action_graphed
     obs = env.reset()
     pipe = S.OverlappedActorLearner(agent, env, done_flag_mode=1) if args.overlap else None
@@ -122,6 +124,7 @@ def main(argv=None):
     sec = float(ms.item()) * 1e-3
     summary = {"example": "train_sac", "n_gpus": world, "envs_total": args.envs, "iters": args.iters,
                "updates_per_iter": args.updates_per_iter, "cuda_graph": not args.no_graph, "overlap": bool(args.overlap),
+               "policy_precision": args.policy_precision,
                "env_steps_per_s": args.iters * args.envs / sec,
                "updates_per_s_per_replica": args.iters * args.updates_per_iter / sec,
                "ms_per_iter": 1e3 * sec / args.iters, "episodes": stats["episodes"],

@@ -178,7 +178,7 @@ class ContinuousAgent:
     """agent/continuous_agent.py:9-154 on the GPU-resident env and replay ring."""
 
     def __init__(self, config, experiment_dir, input_dims, env, device=None, seed=0, use_cuda_graph=True,
-                 memory=None):
+                 memory=None, policy_precision="fp32"):
         if not torch.cuda.is_available():
             raise RuntimeError("sac_agent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.env = env
@@ -198,6 +198,9 @@ class ContinuousAgent:
         self.actor, self.critic_1, self.critic_2 = L.actor, L.critic_1, L.critic_2
         self.value, self.target_value = L.value, L.target_value
         self.use_cuda_graph = bool(use_cuda_graph)
+        if policy_precision not in ("fp32", "tf32", "bf16"):
+            raise ValueError("policy_precision: fp32, tf32 or bf16")
+        self.policy_precision = policy_precision   # dense layers of choose_action on tensor-core inputs (acting only)
         B, O, A = self.batch_size, int(np.prod(self.input_dims)), self.get_n_actions()
         kw = dict(dtype=torch.float32, device=self.device)
         # static inputs of the captured update: sample_buffer writes them in place
@@ -228,7 +231,7 @@ class ContinuousAgent:
         tensor [N, n_actions]; a numpy observation of ONE env gives a numpy action like the reference."""
         if isinstance(observation, torch.Tensor):
             obs = observation.to(device=self.device, dtype=torch.float32)
-            return self.actor.sample_normal(obs.reshape(-1, *self.input_dims), reparameterize=False)[0]
+            return self.actor.act(obs.reshape(-1, *self.input_dims), self.policy_precision)
         state = torch.as_tensor(np.array([observation]), dtype=torch.float32, device=self.device)
         actions, _ = self.actor.sample_normal(state, reparameterize=False)
         return actions.cpu().numpy()[0]
@@ -375,14 +378,15 @@ class OverlappedActorLearner:
     @torch.no_grad()
     def _act(self, k):
         obs = self.env.obs
+        prec = self.agent.policy_precision
         if not self.agent.use_cuda_graph:
-            return self.acting[k].sample_normal(obs, reparameterize=False)[0]
+            return self.acting[k].act(obs, prec)
         if self._policy[k] is None:
             for _ in range(2):
-                self.acting[k].sample_normal(obs, reparameterize=False)
+                self.acting[k].act(obs, prec)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                out = self.acting[k].sample_normal(obs, reparameterize=False)[0]
+                out = self.acting[k].act(obs, prec)
             self._policy[k] = (g, out)
         self._policy[k][0].replay()
         return self._policy[k][1]

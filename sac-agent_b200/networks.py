@@ -98,10 +98,31 @@ class ActorNetwork(BaseNetwork):
         prob = F.relu(self.fc2(prob))
         return self.mean(prob), self.std(prob)
 
-    def sample_normal(self, state, reparameterize=True, eps=None):
+    def act(self, state, precision="fp32"):
+        """A non-reparameterised action for every row of `state` without gradients (what choose_action
+        needs).  precision "tf32" / "bf16" runs the three dense layers on the tensor cores through cuBLAS
+        (acting over ~1e6 envs is GEMM bound in fp32); the head stays fp32.  The learner never uses this."""
+        with torch.no_grad():
+            if precision == "fp32":
+                return self.sample_normal(state, reparameterize=False)[0]
+            if precision == "bf16":
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    mean, std = self.forward(state)
+            elif precision == "tf32":
+                prev = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = True
+                try:
+                    mean, std = self.forward(state)
+                finally:
+                    torch.backends.cuda.matmul.allow_tf32 = prev
+            else:
+                raise ValueError("precision: fp32, tf32 or bf16")
+            return self.sample_normal(state, reparameterize=False, heads=(mean.float(), std.float()))[0]
+
+    def sample_normal(self, state, reparameterize=True, eps=None, heads=None):
         """networks.py:47-70.  `eps` (standard-normal, shape [B, n_actions]) replaces the draw -- the
-        parity tests inject the reference's noise through it."""
-        mean, std = self.forward(state)
+        parity tests inject the reference's noise through it.  `heads` = (mean, std) already computed."""
+        mean, std = self.forward(state) if heads is None else heads
         if eps is None:
             eps = torch.randn_like(mean)
         if mean.is_cuda and mean.dtype == torch.float32 and (reparameterize or not torch.is_grad_enabled()):

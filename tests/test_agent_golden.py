@@ -268,3 +268,25 @@ def test_device_adam_matches_torch_adam_and_polyak():
         assert (p.detach() - q).abs().max().item() <= 1e-6 + 1e-3 * lr * 25
     for t, u in zip(tgt_ref, tgt_ours):
         assert (t - u).abs().max().item() <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol", [("tf32", 5e-3), ("bf16", 5e-2)])
+def test_reduced_precision_acting_stays_close_to_fp32(precision, tol):
+    """choose_action with tensor-core inputs (acting only): same noise, actions within the rounding of the
+    input format of the fp32 policy."""
+    cfg = S.load_config()
+    env = type("E", (), {"action_space": S.Box(low=-1, high=1, dtype=np.float32)})()
+    mem = S.ReplayBuffer(2048, (11,), 1, precision="fp32", device=0, as_torch=True)
+    agent = ContinuousAgent(cfg, None, (11,), env, device=0, memory=mem, policy_precision=precision)
+    obs = torch.rand(4096, 11, device="cuda")
+    torch.manual_seed(7)
+    a_lo = agent.choose_action(obs)
+    agent.policy_precision = "fp32"
+    torch.manual_seed(7)
+    a_hi = agent.choose_action(obs)
+    assert a_lo.dtype == torch.float32 and a_lo.shape == (4096, 1)
+    assert (a_lo - a_hi).abs().max().item() < tol and not torch.equal(a_lo, a_hi)
+    with pytest.raises(ValueError):
+        ContinuousAgent(cfg, None, (11,), env, device=0, memory=mem, policy_precision="fp8")
+    mem.close()
