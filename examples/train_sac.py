@@ -51,7 +51,7 @@ def main(argv=None):
                          "terminations.csv; main.py:116-133) under this directory, one experiment per rank")
     ap.add_argument("--tune", action="store_true",
                     help="population mode (main.py -p): every rank trains with its own tuned_configs.yaml draw")
-    ap.add_argument("--policy-precision", default="fp32", choices=["fp32", "tf32", "bf16"],
+    ap.add_argument("--policy-precision", default="fp32", choices=["fp32", "tf32", "bf16", "tcgen05"],
                     help="dense layers of choose_action on tensor-core inputs (acting only; the learner stays fp32)")
     ap.add_argument("--overlap", action="store_true",
                     help="acting and learning on two streams (OverlappedActorLearner: the policy lags one update)")

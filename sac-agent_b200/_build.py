@@ -30,6 +30,7 @@ UNITS = {
     "replay.cu": [],
     "toys.cu": ["-fmad=false"],
     "agent_ops.cu": [],
+    "policy_mlp.cu": [],
 }
 
 

@@ -198,9 +198,13 @@ class ContinuousAgent:
         self.actor, self.critic_1, self.critic_2 = L.actor, L.critic_1, L.critic_2
         self.value, self.target_value = L.value, L.target_value
         self.use_cuda_graph = bool(use_cuda_graph)
-        if policy_precision not in ("fp32", "tf32", "bf16"):
-            raise ValueError("policy_precision: fp32, tf32 or bf16")
-        self.policy_precision = policy_precision   # dense layers of choose_action on tensor-core inputs (acting only)
+        if policy_precision not in ("fp32", "tf32", "bf16", "tcgen05"):
+            raise ValueError("policy_precision: fp32, tf32, bf16 or tcgen05")
+        # acting only: "tf32" / "bf16" run the policy's dense layers through cuBLAS on tensor-core inputs;
+        # "tcgen05" is libboatenv's fused kernel (csrc/policy_mlp.cu: bf16 inputs, fp32 accumulation, the
+        # whole forward pass and the draw in one launch, weights re-packed after every update)
+        self.policy_precision = policy_precision
+        self._tc_policy = None
         B, O, A = self.batch_size, int(np.prod(self.input_dims)), self.get_n_actions()
         kw = dict(dtype=torch.float32, device=self.device)
         # static inputs of the captured update: sample_buffer writes them in place
@@ -231,14 +235,26 @@ class ContinuousAgent:
         tensor [N, n_actions]; a numpy observation of ONE env gives a numpy action like the reference."""
         if isinstance(observation, torch.Tensor):
             obs = observation.to(device=self.device, dtype=torch.float32)
+            if self.policy_precision == "tcgen05":
+                return self.tensor_core_policy().act(obs.reshape(-1, *self.input_dims).contiguous())
             return self.actor.act(obs.reshape(-1, *self.input_dims), self.policy_precision)
         state = torch.as_tensor(np.array([observation]), dtype=torch.float32, device=self.device)
         actions, _ = self.actor.sample_normal(state, reparameterize=False)
         return actions.cpu().numpy()[0]
 
+    def tensor_core_policy(self):
+        """The fused tcgen05 policy of this agent's actor (created on first use; `learn()` keeps its packed
+        weights current)."""
+        if self._tc_policy is None:
+            from .networks import TensorCorePolicy
+            self._tc_policy = TensorCorePolicy(self.actor, seed=0x5ac)
+        return self._tc_policy
+
     def choose_action_graphed(self, observation):
         """`choose_action` for a PERSISTENT observation tensor (BatchedBoatEnv.obs): the policy's forward
         pass is captured once per tensor and replayed; the result lives in a static output tensor."""
+        if self.policy_precision == "tcgen05":   # already one launch (and its Philox counter is a launch argument)
+            return self.choose_action(observation)
         key = (observation.data_ptr(), tuple(observation.shape))
         entry = self._act_graphs.get(key)
         if entry is None:
@@ -279,6 +295,8 @@ class ContinuousAgent:
                 self._capture()
             self._graph.replay()
         self.updates += 1
+        if self._tc_policy is not None:
+            self._tc_policy.refresh()   # the packed bf16 copy follows the actor
         return self._losses
 
     def learn(self):
@@ -379,6 +397,16 @@ class OverlappedActorLearner:
     def _act(self, k):
         obs = self.env.obs
         prec = self.agent.policy_precision
+        if prec == "tcgen05":
+            if self._policy[k] is None:
+                from .networks import TensorCorePolicy
+                self._policy[k] = TensorCorePolicy(self.acting[k], seed=0x5ac + k)
+                self._policy[k].steps = k   # the two copies draw from interleaved Philox counters
+            pol = self._policy[k]
+            pol.refresh()                   # acting[k] was just published into (stream-ordered after the copy)
+            out = pol.act(obs)
+            pol.steps += 1                  # act() advanced by one: keep the copies interleaved
+            return out
         if not self.agent.use_cuda_graph:
             return self.acting[k].act(obs, prec)
         if self._policy[k] is None:

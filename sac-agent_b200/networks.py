@@ -173,3 +173,65 @@ class ValueNetwork(BaseNetwork):
         x = F.relu(self.fc1(state))
         x = F.relu(self.fc2(x))
         return self.v(x)
+
+
+class TensorCorePolicy:
+    """choose_action over N envs as ONE tcgen05 kernel (csrc/policy_mlp.cu): the actor's three dense layers
+    with bf16 inputs / fp32 accumulation and the tanh-squashed draw, a 128-env tile staying on chip from
+    the observations to the actions.  Holds the packed bf16 copy of the actor's weights; call `refresh()`
+    after the learner changed them.  Acting only -- the learner never uses it."""
+
+    BLOB_BYTES = 256 * 16 * 2 + 256 * 256 * 2 + 16 * 256 * 2 + 256 * 4 + 256 * 4 + 16 * 4
+
+    def __init__(self, actor: ActorNetwork, seed=0):
+        from . import _lib
+        self._lib, self._L = _lib, _lib.lib()
+        self.actor, self.seed = actor, int(seed)
+        w1 = actor.fc1.weight
+        self.obs_dim, self.n_actions = w1.shape[1], actor.mean.weight.shape[0]
+        if w1.shape[0] != 256 or actor.fc2.weight.shape != (256, 256) or self.obs_dim > 16 or self.n_actions > 8:
+            raise ValueError("TensorCorePolicy: 256-wide layers, obs_dim <= 16, n_actions <= 8")
+        if not w1.is_cuda:
+            raise RuntimeError("TensorCorePolicy needs the actor on a CUDA device")
+        self.blob = torch.empty(self.BLOB_BYTES, dtype=torch.uint8, device=w1.device)
+        self.steps = 0
+        self.refresh()
+
+    @staticmethod
+    def _cores(w, rows, cols):
+        """[r, k] fp32 -> zero-padded [rows, cols] bf16 in 8x8 core-matrix order [cols / 8][rows][8], as bytes."""
+        p = torch.zeros((rows, cols), dtype=torch.bfloat16, device=w.device)
+        p[: w.shape[0], : w.shape[1]] = w.to(torch.bfloat16)
+        return p.view(rows, cols // 8, 8).permute(1, 0, 2).contiguous().view(torch.uint8).reshape(-1)
+
+    @torch.no_grad()
+    def refresh(self):
+        a = self.actor
+        heads_w = torch.cat([a.mean.weight, a.std.weight], 0)
+        b3 = torch.zeros(16, dtype=torch.float32, device=self.blob.device)
+        b3[: 2 * self.n_actions] = torch.cat([a.mean.bias, a.std.bias], 0)
+        parts = [self._cores(a.fc1.weight, 256, 16), self._cores(a.fc2.weight, 256, 256), self._cores(heads_w, 16, 256),
+                 a.fc1.bias.float().contiguous().view(torch.uint8), a.fc2.bias.float().contiguous().view(torch.uint8),
+                 b3.view(torch.uint8)]
+        self.blob.copy_(torch.cat(parts))
+
+    @torch.no_grad()
+    def act(self, obs, eps=None, out=None):
+        """obs float32 [N, obs_dim] (contiguous, on the actor's device) -> actions float32 [N, n_actions].
+        eps: optional standard-normal draws [N, n_actions]; otherwise Philox(seed; env, call number)."""
+        n = obs.shape[0]
+        if obs.dtype != torch.float32 or not obs.is_contiguous() or obs.shape[1] != self.obs_dim:
+            raise ValueError("obs: contiguous float32 [N, obs_dim]")
+        if out is None:
+            out = torch.empty((n, self.n_actions), dtype=torch.float32, device=obs.device)
+        if eps is not None:
+            eps = eps.to(torch.float32).contiguous()
+        with torch.cuda.device(obs.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            self._lib.check(self._L.boatagent_policy_act(self.blob.data_ptr(), obs.data_ptr(),
+                                                         None if eps is None else eps.data_ptr(),
+                                                         self.actor.max_action.data_ptr(), self.seed, self.steps, n,
+                                                         self.obs_dim, self.n_actions, out.data_ptr(), stream),
+                            "boatagent_policy_act")
+        self.steps += 1
+        return out

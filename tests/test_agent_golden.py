@@ -271,6 +271,56 @@ def test_device_adam_matches_torch_adam_and_polyak():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,n_actions,obs_dim", [(1, 1, 11), (127, 1, 11), (128, 1, 11), (1000, 2, 16), (70_001, 1, 11),
+                                                  (300, 8, 5)])
+def test_tcgen05_policy_matches_bf16_emulation(n, n_actions, obs_dim):
+    """csrc/policy_mlp.cu against the same arithmetic spelled out in PyTorch (operands rounded to bf16, fp32
+    accumulation, fp32 head) and against the fp32 policy; ragged tiles, several tiles per CTA, padded shapes."""
+    from sac_agent_b200.networks import ActorNetwork, TensorCorePolicy
+    torch.manual_seed(n)
+    max_a = np.linspace(1.0, 0.5, n_actions).astype(np.float32)
+    actor = ActorNetwork(None, (obs_dim,), max_a, n_actions=n_actions).cuda()
+    pol = TensorCorePolicy(actor)
+    obs, eps = torch.rand(n, obs_dim, device="cuda"), torch.randn(n, n_actions, device="cuda")
+    got = pol.act(obs, eps)
+    bf = lambda t: t.to(torch.bfloat16).float()  # noqa: E731
+    with torch.no_grad():
+        h = bf(torch.relu(bf(obs) @ bf(actor.fc1.weight).T + actor.fc1.bias))
+        h = bf(torch.relu(h @ bf(actor.fc2.weight).T + actor.fc2.bias))
+        mean, raw = h @ bf(actor.mean.weight).T + actor.mean.bias, h @ bf(actor.std.weight).T + actor.std.bias
+        emu = torch.tanh(mean + eps * torch.exp(-5.0 + 3.5 * (torch.tanh(raw) + 1.0))) * actor.max_action
+        ref = actor.sample_normal(obs, reparameterize=False, eps=eps)[0]
+    assert got.shape == (n, n_actions)
+    assert (got - emu).abs().max().item() < 2e-3     # accumulation order and bf16 re-rounding of near-ties
+    assert (got - ref).abs().max().item() < 3e-2     # bf16 inputs against the fp32 policy
+    # without eps: Philox draws, a fresh set per call, reproducible per (seed, call number)
+    k = pol.steps
+    a1, a2 = pol.act(obs).clone(), pol.act(obs).clone()
+    pol.steps = k + 1
+    assert not torch.equal(a1, a2) and torch.equal(pol.act(obs), a2)
+    # the packed weights follow the actor after refresh()
+    with torch.no_grad():
+        actor.mean.bias.add_(0.5)
+    stale = pol.act(obs, eps)
+    pol.refresh()
+    assert torch.equal(stale, got) and not torch.equal(pol.act(obs, eps), got)
+
+
+@pytest.mark.gpu
+def test_tcgen05_policy_draws_are_standard_normal():
+    from sac_agent_b200.networks import ActorNetwork, TensorCorePolicy
+    actor = ActorNetwork(None, (11,), np.array([1.0], dtype=np.float32), n_actions=1).cuda()
+    with torch.no_grad():   # mean 0, log_std = -5 + 3.5 * (tanh(0) + 1) = -1.5: action = tanh(e * exp(-1.5))
+        for layer in (actor.mean, actor.std):
+            layer.weight.zero_(); layer.bias.zero_()
+    pol = TensorCorePolicy(actor, seed=3)
+    a = pol.act(torch.rand(400_000, 11, device="cuda"))
+    e = torch.atanh(a.double()) / np.exp(-1.5)
+    assert abs(e.mean().item()) < 0.01 and abs(e.std().item() - 1.0) < 0.01
+    assert abs((e ** 4).mean().item() - 3.0) < 0.1
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("precision,tol", [("tf32", 5e-3), ("bf16", 5e-2)])
 def test_reduced_precision_acting_stays_close_to_fp32(precision, tol):
     """choose_action with tensor-core inputs (acting only): same noise, actions within the rounding of the
