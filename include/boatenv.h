@@ -268,12 +268,13 @@ BOATENV_API int boatagent_adam_polyak_step(const boatagent_adam_slot *slots_host
 /* choose_action (continuous_agent.py:57-61) for n envs in one tcgen05 kernel: ActorNetwork.forward
  * (networks.py:38-45, three 256-wide dense layers, bf16 inputs / fp32 accumulation) and the
  * non-reparameterised tanh-squashed draw (:47-65).  weight_blob: BOATAGENT_POLICY_BLOB_BYTES device
- * bytes, 16-byte aligned: the bf16 weights in 8x8 core-matrix order -- element (row, k) of an
- * R-row matrix at (k / 8) * (R * 16) + row * 16 + (k % 8) * 2 -- as [fc1 256 x 16 (obs_dim zero
- * padded)][fc2 256 x 256][heads 16 x 256 (mean rows, then std rows, zero padded)], followed by the
- * fp32 biases [256][256][16].  obs float32 [n][obs_dim] (obs_dim <= 16); eps float32 [n][n_actions]
- * standard-normal draws or NULL (then Philox(seed; env, step) + Box-Muller); n_actions <= 8. */
-#define BOATAGENT_POLICY_BLOB_BYTES (256 * 16 * 2 + 256 * 256 * 2 + 16 * 256 * 2 + 256 * 4 + 256 * 4 + 16 * 4)
+ * bytes, 16-byte aligned: [fc1 256 x 16 (obs_dim zero padded)][fc2 256 x 256] as bf16 in 8x8
+ * core-matrix order -- element (row, k) of an R-row matrix at (k / 8) * (R * 16) + row * 16 +
+ * (k % 8) * 2 --, then the heads as fp32 [16][256] row-major (mean rows, then std rows, zero
+ * padded), then the fp32 biases [256][256][16].  obs float32 [n][obs_dim] (obs_dim <= 16); eps
+ * float32 [n][n_actions] standard-normal draws or NULL (then Philox(seed; env, step) + Box-Muller);
+ * n_actions 1, 2, 4 or 8. */
+#define BOATAGENT_POLICY_BLOB_BYTES (256 * 16 * 2 + 256 * 256 * 2 + 16 * 256 * 4 + 256 * 4 + 256 * 4 + 16 * 4)
 BOATENV_API int boatagent_policy_act(const void *weight_blob, const float *obs, const float *eps,
                          const float *max_action, uint64_t seed, uint64_t step, int64_t n, int32_t obs_dim,
                          int32_t n_actions, float *action_out, void *stream);

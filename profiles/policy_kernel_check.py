@@ -16,9 +16,9 @@ for n in (1, 100, 128, 1000, 65536):
         # bf16-input emulation
         bf = lambda t: t.to(torch.bfloat16).float()
         h = bf(torch.relu(bf(obs) @ bf(actor.fc1.weight).T + actor.fc1.bias))
-        h = bf(torch.relu(h @ bf(actor.fc2.weight).T + actor.fc2.bias))
-        mean = h @ bf(actor.mean.weight).T + actor.mean.bias
-        raw = h @ bf(actor.std.weight).T + actor.std.bias
+        h = torch.relu(h @ bf(actor.fc2.weight).T + actor.fc2.bias)
+        mean = h @ actor.mean.weight.T + actor.mean.bias
+        raw = h @ actor.std.weight.T + actor.std.bias
         emu = torch.tanh(mean + eps*torch.exp(-5+3.5*(torch.tanh(raw)+1)))
     print(n, 'vs fp32', (a-ref).abs().max().item(), 'vs bf16 emu', (a-emu).abs().max().item(), flush=True)
 n=1<<20

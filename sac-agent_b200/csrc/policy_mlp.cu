@@ -9,9 +9,12 @@
 // on chip from the observations to the actions:
 //   * all weights (bf16, 144 kB) live in shared memory for the life of the CTA, in the K-major
 //     no-swizzle core-matrix layout the UMMA descriptors address directly;
-//   * layer l is tcgen05.mma (M = 128 envs, N = 256 / 16, K steps of 16) into TMEM; four epilogue warps
-//     read the accumulator back (tcgen05.ld, one TMEM lane = one env), add the bias, apply ReLU, round to
-//     bf16 and write the tile as the A operand of the next layer;
+//   * the two hidden layers are tcgen05.mma (M = 128 envs, N = 256, K steps of 16) into TMEM; eight epilogue
+//     warps read the accumulators back (tcgen05.ld, one TMEM lane = one env, half a row per thread): after
+//     layer 1 they add the bias, apply ReLU, round to bf16 and write the tile as the A operand of layer 2;
+//     after layer 2 the fp32 activations go straight from registers into the dot products of the two heads
+//     (fp32 weights), the draw and the squash -- the heads never leave the registers;
+//   * the next tile's observations are fetched while the current tile computes;
 //   * HBM traffic is the input and the output: 4 * obs_dim + 4 * A bytes per env.
 // Inputs are rounded to bf16 (fp32 accumulation): acting only, the learner never sees this kernel.
 #include <cstdint>
@@ -25,19 +28,23 @@
 namespace {
 
 constexpr int kHidden = 256, kTileM = 128, kK1 = 16, kN3 = 16;
-constexpr int kEpiThreads = 128, kThreads = kEpiThreads + 32;
+// 8 epilogue warps: warp w works on TMEM lanes 32 (w % 4) .. + 31 (the hardware's lane window of a warp), i.e. on
+// env row 32 (w % 4) + lane, and on the accumulator columns 128 (w / 4) .. + 127 of that row; warp 8 issues the MMAs.
+constexpr int kEpiThreads = 256, kThreads = kEpiThreads + 32, kMmaWarp = kEpiThreads / 32;
 // shared-memory map (bytes).  Operand layout: element (row, k) of an R-row operand sits at
 // (k / 8) * (R * 16) + row * 16 + (k % 8) * 2  -- 8x8 core matrices, K-adjacent cores R*16 bytes apart (LBO),
 // row groups 128 bytes apart (SBO).
 constexpr int kOffW1 = 0;                                   // [256 rows][16]
 constexpr int kOffW2 = kOffW1 + kHidden * kK1 * 2;          // [256 rows][256]
-constexpr int kOffW3 = kOffW2 + kHidden * kHidden * 2;      // [16 rows][256]
-constexpr int kOffB1 = kOffW3 + kN3 * kHidden * 2;          // fp32[256]
+constexpr int kOffW3 = kOffW2 + kHidden * kHidden * 2;      // fp32 [16 rows][256], row-major: the heads stay in fp32
+constexpr int kOffB1 = kOffW3 + kN3 * kHidden * 4;          // fp32[256]
 constexpr int kOffB2 = kOffB1 + kHidden * 4;
 constexpr int kOffB3 = kOffB2 + kHidden * 4;                // fp32[16]
 constexpr int kBlobBytes = kOffB3 + kN3 * 4;                // what the host packs (BOATAGENT_POLICY_BLOB_BYTES)
 constexpr int kOffA0 = (kBlobBytes + 127) / 128 * 128;      // [128 rows][16]
 constexpr int kOffA1 = kOffA0 + kTileM * kK1 * 2;           // [128 rows][256]
+constexpr int kOffPart = kOffA1;                            // fp32 [128 rows][16]: head partial sums of the upper column half
+                                                            // (aliases A1: layer 2 has finished reading it by then)
 constexpr int kOffBar = kOffA1 + kTileM * kHidden * 2;
 constexpr int kSmemBytes = kOffBar + 16;
 static_assert(kBlobBytes == BOATAGENT_POLICY_BLOB_BYTES, "header and kernel disagree on the weight blob");
@@ -101,10 +108,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<const uint32_t *>(&p);
 }
 
-// One hidden layer's epilogue for the thread's row: accumulator -> + bias -> ReLU -> bf16 -> A operand tile.
-__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float *bias, unsigned char *a1, int row) {
+// Layer-1 epilogue for the thread's half row (columns col0 .. col0 + 127): accumulator -> + bias -> ReLU -> bf16 ->
+// A operand tile of layer 2.
+__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float *bias, unsigned char *a1, int row, int col0) {
 #pragma unroll 1
-    for (int c = 0; c < kHidden / 32; ++c) {
+    for (int c = col0 / 32; c < col0 / 32 + 4; ++c) {
         float v[32];
         tmem_ld32(tmem_row + (uint32_t)(c * 32), v);
 #pragma unroll
@@ -120,13 +128,45 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float *
     }
 }
 
+// Layer-2 epilogue fused with the two heads: h2 = relu(acc + bias) stays in fp32 registers and goes straight into
+// the 2 * n_actions dot products with the fp32 head weights (shared memory, broadcast reads).  acc[j] += partial sums
+// over this thread's 128 columns.
+template <int NH>
+__device__ __forceinline__ void heads_epilogue(uint32_t tmem_row, const float *bias, const float *w3, int col0, float (&acc)[NH]) {
+#pragma unroll
+    for (int j = 0; j < NH; ++j) acc[j] = 0.f;
+#pragma unroll 1
+    for (int c = col0 / 32; c < col0 / 32 + 4; ++c) {
+        float v[32];
+        tmem_ld32(tmem_row + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[c * 32 + i], 0.f);
+#pragma unroll
+        for (int j = 0; j < NH; ++j) {
+            const float4 *w = reinterpret_cast<const float4 *>(w3 + j * kHidden + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 ww = w[i];
+                acc[j] = fmaf(v[4 * i + 0], ww.x, acc[j]);
+                acc[j] = fmaf(v[4 * i + 1], ww.y, acc[j]);
+                acc[j] = fmaf(v[4 * i + 2], ww.z, acc[j]);
+                acc[j] = fmaf(v[4 * i + 3], ww.w, acc[j]);
+            }
+        }
+    }
+}
+
+template <int NA>   // NA = n_actions (1, 2, 4 or 8 instantiated)
 __global__ void __launch_bounds__(kThreads, 1)
 policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restrict__ obs, const float *__restrict__ eps,
                   const float *__restrict__ max_action, unsigned long long seed, unsigned long long step, long long n,
-                  int obs_dim, int n_actions, float *__restrict__ action_out) {
+                  int obs_dim, float *__restrict__ action_out) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t tmem_base_slot;
+    constexpr int NH = 2 * NA;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = (warp & 3) * 32 + lane;      // env row of the tile this epilogue thread works on
+    const int col0 = (warp >> 2) * 128;          // its half of the accumulator columns (epilogue warps only)
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kOffBar);
 
     // ---- one-time setup: weights into shared memory, barrier, TMEM ----
@@ -136,7 +176,7 @@ policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restric
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {   // the MMA warp owns the 512 TMEM columns (two 128 x 256 fp32 accumulators)
+    if (warp == kMmaWarp) {   // the MMA warp owns the 512 TMEM columns (two 128 x 256 fp32 accumulators)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -145,21 +185,27 @@ policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restric
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp & 3) * 32u << 16);   // lanes 32w .. 32w+31 belong to warp w
+    const uint32_t tmem_row = tmem + ((uint32_t)(warp & 3) * 32u << 16);
     const uint32_t sbase = smem_addr(smem);
     const float *b1 = reinterpret_cast<const float *>(smem + kOffB1), *b2 = reinterpret_cast<const float *>(smem + kOffB2),
-                *b3 = reinterpret_cast<const float *>(smem + kOffB3);
+                *b3 = reinterpret_cast<const float *>(smem + kOffB3), *w3 = reinterpret_cast<const float *>(smem + kOffW3);
     unsigned char *a0 = smem + kOffA0, *a1 = smem + kOffA1;
+    float *part = reinterpret_cast<float *>(smem + kOffPart);
     uint32_t parity = 0;
 
     const long long n_tiles = (n + kTileM - 1) / kTileM;
+    // the observation row of the NEXT tile is fetched while the current one computes (warps 0-3: one row each)
+    float o[kK1];
+    auto fetch_obs = [&](long long t) {
+        const long long e = t * kTileM + row;
+#pragma unroll
+        for (int q = 0; q < kK1; ++q) o[q] = (q < obs_dim && t < n_tiles && e < n) ? __ldg(obs + e * obs_dim + q) : 0.f;
+    };
+    if (warp < 4) fetch_obs(blockIdx.x);
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long env = tile * kTileM + tid;   // epilogue thread tid = row tid of the tile
+        const long long env = tile * kTileM + row;
         // ---- observations -> bf16 A0 [128][16] ----
         if (warp < 4) {
-            float o[kK1];
-#pragma unroll
-            for (int q = 0; q < kK1; ++q) o[q] = (q < obs_dim && env < n) ? __ldg(obs + env * obs_dim + q) : 0.f;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 uint4 out;
@@ -167,30 +213,31 @@ policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restric
                 out.y = pack_bf16(o[j * 8 + 2], o[j * 8 + 3]);
                 out.z = pack_bf16(o[j * 8 + 4], o[j * 8 + 5]);
                 out.w = pack_bf16(o[j * 8 + 6], o[j * 8 + 7]);
-                *reinterpret_cast<uint4 *>(a0 + j * (kTileM * 16) + tid * 16) = out;
+                *reinterpret_cast<uint4 *>(a0 + j * (kTileM * 16) + row * 16) = out;
             }
             proxy_fence();
+            fetch_obs(tile + gridDim.x);
         }
         tc_fence_before();
         __syncthreads();
         // ---- layer 1: D1[128][256] = A0 . W1^T (one K step) ----
-        if (warp == 4 && lane == 0) {
+        if (warp == kMmaWarp && lane == 0) {
             tc_fence_after();
             umma_bf16(tmem, umma_desc(sbase + kOffA0, kTileM * 16, 128), umma_desc(sbase + kOffW1, kHidden * 16, 128),
                       umma_idesc(kTileM, kHidden), 0u);
             umma_commit(bar);
         }
-        if (warp < 4) {
+        if (warp < kMmaWarp) {
             bar_wait(bar, parity);
             tc_fence_after();
-            hidden_epilogue(tmem_row, b1, a1, tid);
+            hidden_epilogue(tmem_row, b1, a1, row, col0);
             proxy_fence();
         }
         parity ^= 1u;
         tc_fence_before();
         __syncthreads();
         // ---- layer 2: D2[128][256] = A1 . W2^T (16 K steps) ----
-        if (warp == 4 && lane == 0) {
+        if (warp == kMmaWarp && lane == 0) {
             tc_fence_after();
 #pragma unroll 1
             for (int k = 0; k < kHidden / 16; ++k)
@@ -199,37 +246,26 @@ policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restric
                           umma_idesc(kTileM, kHidden), k > 0 ? 1u : 0u);
             umma_commit(bar);
         }
-        if (warp < 4) {
+        if (warp < kMmaWarp) {
             bar_wait(bar, parity);
             tc_fence_after();
-            hidden_epilogue(tmem_row + 256u, b2, a1, tid);   // layer 2 is done reading A1: overwrite it in place
-            proxy_fence();
-        }
-        parity ^= 1u;
-        tc_fence_before();
-        __syncthreads();
-        // ---- heads: D3[128][16] = A1 . W3^T (rows of W3: mean heads, then std heads, zero padding) ----
-        if (warp == 4 && lane == 0) {
-            tc_fence_after();
-#pragma unroll 1
-            for (int k = 0; k < kHidden / 16; ++k)
-                umma_bf16(tmem, umma_desc(sbase + kOffA1 + k * 2 * (kTileM * 16), kTileM * 16, 128),
-                          umma_desc(sbase + kOffW3 + k * 2 * (kN3 * 16), kN3 * 16, 128), umma_idesc(kTileM, kN3),
-                          k > 0 ? 1u : 0u);
-            umma_commit(bar);
-        }
-        if (warp < 4) {
-            bar_wait(bar, parity);
-            tc_fence_after();
-            float v[32];
-            tmem_ld32(tmem_row, v);   // columns 0..15 are the heads (16..31: stale layer-1 columns, ignored)
-            if (env < n) {
-                for (int a = 0; a < n_actions; ++a) {   // sample_normal, networks.py:47-65
-                    const float mean = v[a] + b3[a];
-                    const float log_std = -5.0f + 3.5f * (tanhf(v[n_actions + a] + b3[n_actions + a]) + 1.0f);
+            // ---- layer-2 epilogue + heads (fp32): rows of w3 are the mean heads, then the std heads ----
+            float acc[NH];
+            heads_epilogue<NH>(tmem_row + 256u, b2, w3, col0, acc);
+            if (col0 != 0) {
+#pragma unroll
+                for (int j = 0; j < NH; ++j) part[row * kN3 + j] = acc[j];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
+            if (col0 == 0 && env < n) {
+#pragma unroll
+                for (int a = 0; a < NA; ++a) {   // sample_normal, networks.py:47-65
+                    const float mean = acc[a] + part[row * kN3 + a] + b3[a];
+                    const float raw = acc[NA + a] + part[row * kN3 + NA + a] + b3[NA + a];
+                    const float log_std = -5.0f + 3.5f * (tanhf(raw) + 1.0f);
                     float e;
                     if (eps) {
-                        e = __ldg(eps + env * n_actions + a);
+                        e = __ldg(eps + env * NA + a);
                     } else {   // Box-Muller on Philox(seed; env, step, action)
                         const boatenv::Philox4 r = boatenv::philox4x32_10(
                             (uint32_t)env, (uint32_t)((unsigned long long)env >> 32), (uint32_t)step,
@@ -239,16 +275,16 @@ policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restric
                         const float u2 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
                         e = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
                     }
-                    action_out[env * n_actions + a] = tanhf(mean + e * expf(log_std)) * __ldg(max_action + a);
+                    action_out[env * NA + a] = tanhf(mean + e * expf(log_std)) * __ldg(max_action + a);
                 }
             }
         }
         parity ^= 1u;
         tc_fence_before();
-        __syncthreads();   // D3 / A0 / A1 are free for the next tile
+        __syncthreads();   // accumulators, A0, A1 and the partial sums are free for the next tile
         tc_fence_after();
     }
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 }  // namespace
@@ -257,23 +293,36 @@ extern "C" int boatagent_policy_act(const void *weight_blob, const float *obs, c
                                     uint64_t seed, uint64_t step, int64_t n, int32_t obs_dim, int32_t n_actions,
                                     float *action_out, void *stream) {
     if (!weight_blob || !obs || !max_action || !action_out || n <= 0) return BOATENV_EINVAL;
-    if (obs_dim < 1 || obs_dim > kK1 || n_actions < 1 || 2 * n_actions > kN3) return BOATENV_EUNSUPPORTED;
+    if (obs_dim < 1 || obs_dim > kK1) return BOATENV_EUNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(weight_blob) & 15u) != 0) return BOATENV_EALIGN;
+    using kern_t = void (*)(const unsigned char *, const float *, const float *, const float *, unsigned long long,
+                            unsigned long long, long long, int, float *);
+    kern_t kern = nullptr;
+    switch (n_actions) {   // the head count is a template parameter (its dot products live in registers)
+    case 1: kern = policy_mlp_kernel<1>; break;
+    case 2: kern = policy_mlp_kernel<2>; break;
+    case 4: kern = policy_mlp_kernel<4>; break;
+    case 8: kern = policy_mlp_kernel<8>; break;
+    default: return BOATENV_EUNSUPPORTED;
+    }
     static int n_sm = 0, configured_dev = -1;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     if (configured_dev != dev) {
-        e = cudaFuncSetAttribute(policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) return (int)e;
+        for (kern_t k : {(kern_t)policy_mlp_kernel<1>, (kern_t)policy_mlp_kernel<2>, (kern_t)policy_mlp_kernel<4>,
+                         (kern_t)policy_mlp_kernel<8>}) {
+            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+            if (e != cudaSuccess) return (int)e;
+        }
         e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
         configured_dev = dev;
     }
     const long long tiles = (n + kTileM - 1) / kTileM;
     const unsigned grid = (unsigned)(tiles < n_sm ? tiles : n_sm);
-    policy_mlp_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
-        (const unsigned char *)weight_blob, obs, eps, max_action, seed, step, n, obs_dim, n_actions, action_out);
+    kern<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>((const unsigned char *)weight_blob, obs, eps, max_action, seed,
+                                                              step, n, obs_dim, action_out);
     boatenv::count_launch();
     return (int)cudaGetLastError();
 }

@@ -181,7 +181,7 @@ class TensorCorePolicy:
     the observations to the actions.  Holds the packed bf16 copy of the actor's weights; call `refresh()`
     after the learner changed them.  Acting only -- the learner never uses it."""
 
-    BLOB_BYTES = 256 * 16 * 2 + 256 * 256 * 2 + 16 * 256 * 2 + 256 * 4 + 256 * 4 + 16 * 4
+    BLOB_BYTES = 256 * 16 * 2 + 256 * 256 * 2 + 16 * 256 * 4 + 256 * 4 + 256 * 4 + 16 * 4
 
     def __init__(self, actor: ActorNetwork, seed=0):
         from . import _lib
@@ -189,8 +189,9 @@ class TensorCorePolicy:
         self.actor, self.seed = actor, int(seed)
         w1 = actor.fc1.weight
         self.obs_dim, self.n_actions = w1.shape[1], actor.mean.weight.shape[0]
-        if w1.shape[0] != 256 or actor.fc2.weight.shape != (256, 256) or self.obs_dim > 16 or self.n_actions > 8:
-            raise ValueError("TensorCorePolicy: 256-wide layers, obs_dim <= 16, n_actions <= 8")
+        if (w1.shape[0] != 256 or actor.fc2.weight.shape != (256, 256) or self.obs_dim > 16
+                or self.n_actions not in (1, 2, 4, 8)):
+            raise ValueError("TensorCorePolicy: 256-wide layers, obs_dim <= 16, n_actions 1, 2, 4 or 8")
         if not w1.is_cuda:
             raise RuntimeError("TensorCorePolicy needs the actor on a CUDA device")
         self.blob = torch.empty(self.BLOB_BYTES, dtype=torch.uint8, device=w1.device)
@@ -207,10 +208,11 @@ class TensorCorePolicy:
     @torch.no_grad()
     def refresh(self):
         a = self.actor
-        heads_w = torch.cat([a.mean.weight, a.std.weight], 0)
+        heads_w = torch.zeros((16, 256), dtype=torch.float32, device=self.blob.device)   # fp32, row-major
+        heads_w[: 2 * self.n_actions] = torch.cat([a.mean.weight, a.std.weight], 0)
         b3 = torch.zeros(16, dtype=torch.float32, device=self.blob.device)
         b3[: 2 * self.n_actions] = torch.cat([a.mean.bias, a.std.bias], 0)
-        parts = [self._cores(a.fc1.weight, 256, 16), self._cores(a.fc2.weight, 256, 256), self._cores(heads_w, 16, 256),
+        parts = [self._cores(a.fc1.weight, 256, 16), self._cores(a.fc2.weight, 256, 256), heads_w.view(torch.uint8).reshape(-1),
                  a.fc1.bias.float().contiguous().view(torch.uint8), a.fc2.bias.float().contiguous().view(torch.uint8),
                  b3.view(torch.uint8)]
         self.blob.copy_(torch.cat(parts))
