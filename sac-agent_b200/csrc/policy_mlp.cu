@@ -87,9 +87,9 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
         "D_%=:\n\t"
         "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
-// 32 consecutive fp32 accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// 32 consecutive fp32 accumulator columns of this thread's TMEM lane: asynchronous load (the registers are valid after
+// tmem_ld_wait()), so the next chunk can be in flight while the current one is processed
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -99,9 +99,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// The registers are tied to the wait as in/out operands: nothing that reads them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
@@ -111,21 +118,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // Layer-1 epilogue for the thread's half row (columns col0 .. col0 + 127): accumulator -> + bias -> ReLU -> bf16 ->
 // A operand tile of layer 2.
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float *bias, unsigned char *a1, int row, int col0) {
-#pragma unroll 1
-    for (int c = col0 / 32; c < col0 / 32 + 4; ++c) {
-        float v[32];
-        tmem_ld32(tmem_row + (uint32_t)(c * 32), v);
+    uint32_t ra[32], rb[32];
+    tmem_ld32_issue(tmem_row + (uint32_t)col0, ra);
+    auto chunk = [&](const uint32_t (&r)[32], int c) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {   // four 8-column cores
+            const float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 32 + q * 8);
+            const float4 b1 = *reinterpret_cast<const float4 *>(bias + c * 32 + q * 8 + 4);
             uint4 out;
-            const float *b = bias + c * 32 + q * 8;
-            out.x = pack_bf16(fmaxf(v[q * 8 + 0] + b[0], 0.f), fmaxf(v[q * 8 + 1] + b[1], 0.f));
-            out.y = pack_bf16(fmaxf(v[q * 8 + 2] + b[2], 0.f), fmaxf(v[q * 8 + 3] + b[3], 0.f));
-            out.z = pack_bf16(fmaxf(v[q * 8 + 4] + b[4], 0.f), fmaxf(v[q * 8 + 5] + b[5], 0.f));
-            out.w = pack_bf16(fmaxf(v[q * 8 + 6] + b[6], 0.f), fmaxf(v[q * 8 + 7] + b[7], 0.f));
+            out.x = pack_bf16(fmaxf(__uint_as_float(r[q * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(r[q * 8 + 1]) + b0.y, 0.f));
+            out.y = pack_bf16(fmaxf(__uint_as_float(r[q * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(r[q * 8 + 3]) + b0.w, 0.f));
+            out.z = pack_bf16(fmaxf(__uint_as_float(r[q * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(r[q * 8 + 5]) + b1.y, 0.f));
+            out.w = pack_bf16(fmaxf(__uint_as_float(r[q * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(r[q * 8 + 7]) + b1.w, 0.f));
             *reinterpret_cast<uint4 *>(a1 + (c * 4 + q) * (kTileM * 16) + row * 16) = out;
         }
-    }
+    };
+    const int c0 = col0 / 32;
+    tmem_ld_wait(ra); tmem_ld32_issue(tmem_row + (uint32_t)(col0 + 32), rb); chunk(ra, c0);
+    tmem_ld_wait(rb); tmem_ld32_issue(tmem_row + (uint32_t)(col0 + 64), ra); chunk(rb, c0 + 1);
+    tmem_ld_wait(ra); tmem_ld32_issue(tmem_row + (uint32_t)(col0 + 96), rb); chunk(ra, c0 + 2);
+    tmem_ld_wait(rb); chunk(rb, c0 + 3);
 }
 
 // Layer-2 epilogue fused with the two heads: h2 = relu(acc + bias) stays in fp32 registers and goes straight into
@@ -135,12 +147,18 @@ template <int NH>
 __device__ __forceinline__ void heads_epilogue(uint32_t tmem_row, const float *bias, const float *w3, int col0, float (&acc)[NH]) {
 #pragma unroll
     for (int j = 0; j < NH; ++j) acc[j] = 0.f;
-#pragma unroll 1
-    for (int c = col0 / 32; c < col0 / 32 + 4; ++c) {
+    uint32_t ra[32], rb[32];
+    tmem_ld32_issue(tmem_row + (uint32_t)col0, ra);
+    auto chunk = [&](const uint32_t (&r)[32], int c) {
         float v[32];
-        tmem_ld32(tmem_row + (uint32_t)(c * 32), v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[c * 32 + i], 0.f);
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = *reinterpret_cast<const float4 *>(bias + c * 32 + 4 * i);
+            v[4 * i + 0] = fmaxf(__uint_as_float(r[4 * i + 0]) + b.x, 0.f);
+            v[4 * i + 1] = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
+            v[4 * i + 2] = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f);
+            v[4 * i + 3] = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
+        }
 #pragma unroll
         for (int j = 0; j < NH; ++j) {
             const float4 *w = reinterpret_cast<const float4 *>(w3 + j * kHidden + c * 32);
@@ -153,7 +171,12 @@ __device__ __forceinline__ void heads_epilogue(uint32_t tmem_row, const float *b
                 acc[j] = fmaf(v[4 * i + 3], ww.w, acc[j]);
             }
         }
-    }
+    };
+    const int c0 = col0 / 32;
+    tmem_ld_wait(ra); tmem_ld32_issue(tmem_row + (uint32_t)(col0 + 32), rb); chunk(ra, c0);
+    tmem_ld_wait(rb); tmem_ld32_issue(tmem_row + (uint32_t)(col0 + 64), ra); chunk(rb, c0 + 1);
+    tmem_ld_wait(ra); tmem_ld32_issue(tmem_row + (uint32_t)(col0 + 96), rb); chunk(ra, c0 + 2);
+    tmem_ld_wait(rb); chunk(rb, c0 + 3);
 }
 
 template <int NA>   // NA = n_actions (1, 2, 4 or 8 instantiated)
