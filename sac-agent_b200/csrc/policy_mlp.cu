@@ -197,6 +197,7 @@ policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restric
         reinterpret_cast<uint4 *>(smem)[i] = __ldg(reinterpret_cast<const uint4 *>(blob) + i);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar + 1)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {   // the MMA warp owns the 512 TMEM columns (two 128 x 256 fp32 accumulators)
@@ -217,49 +218,60 @@ policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restric
     uint32_t parity = 0;
 
     const long long n_tiles = (n + kTileM - 1) / kTileM;
-    // the observation row of the NEXT tile is fetched while the current one computes (warps 0-3: one row each)
+    uint64_t *bar1 = bar, *bar2 = bar + 1;   // layer-1 / layer-2 accumulator ready
+    // Software pipeline over the CTA's tiles: layer 1 of tile t + 1 is issued right behind layer 2 of tile t, so it
+    // (and the staging of its observations) runs under the layer-2 epilogue of tile t; the observation rows are
+    // fetched from HBM one more tile ahead (warps 0-3: one row each).
     float o[kK1];
     auto fetch_obs = [&](long long t) {
         const long long e = t * kTileM + row;
 #pragma unroll
         for (int q = 0; q < kK1; ++q) o[q] = (q < obs_dim && t < n_tiles && e < n) ? __ldg(obs + e * obs_dim + q) : 0.f;
     };
-    if (warp < 4) fetch_obs(blockIdx.x);
+    auto stage_obs = [&]() {   // registers -> bf16 A0 [128][16]
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            uint4 out;
+            out.x = pack_bf16(o[j * 8 + 0], o[j * 8 + 1]);
+            out.y = pack_bf16(o[j * 8 + 2], o[j * 8 + 3]);
+            out.z = pack_bf16(o[j * 8 + 4], o[j * 8 + 5]);
+            out.w = pack_bf16(o[j * 8 + 6], o[j * 8 + 7]);
+            *reinterpret_cast<uint4 *>(a0 + j * (kTileM * 16) + row * 16) = out;
+        }
+    };
+    auto issue_layer1 = [&]() {   // D1[128][256] = A0 . W1^T (one K step)
+        umma_bf16(tmem, umma_desc(sbase + kOffA0, kTileM * 16, 128), umma_desc(sbase + kOffW1, kHidden * 16, 128),
+                  umma_idesc(kTileM, kHidden), 0u);
+        umma_commit(bar1);
+    };
+    if (warp < 4) {
+        fetch_obs(blockIdx.x);
+        stage_obs();
+        proxy_fence();
+        fetch_obs((long long)blockIdx.x + gridDim.x);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp && lane == 0) {
+        tc_fence_after();
+        issue_layer1();
+    }
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long env = tile * kTileM + row;
-        // ---- observations -> bf16 A0 [128][16] ----
-        if (warp < 4) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                uint4 out;
-                out.x = pack_bf16(o[j * 8 + 0], o[j * 8 + 1]);
-                out.y = pack_bf16(o[j * 8 + 2], o[j * 8 + 3]);
-                out.z = pack_bf16(o[j * 8 + 4], o[j * 8 + 5]);
-                out.w = pack_bf16(o[j * 8 + 6], o[j * 8 + 7]);
-                *reinterpret_cast<uint4 *>(a0 + j * (kTileM * 16) + row * 16) = out;
-            }
-            proxy_fence();
-            fetch_obs(tile + gridDim.x);
-        }
-        tc_fence_before();
-        __syncthreads();
-        // ---- layer 1: D1[128][256] = A0 . W1^T (one K step) ----
-        if (warp == kMmaWarp && lane == 0) {
-            tc_fence_after();
-            umma_bf16(tmem, umma_desc(sbase + kOffA0, kTileM * 16, 128), umma_desc(sbase + kOffW1, kHidden * 16, 128),
-                      umma_idesc(kTileM, kHidden), 0u);
-            umma_commit(bar);
-        }
+        const bool more = tile + gridDim.x < n_tiles;
         if (warp < kMmaWarp) {
-            bar_wait(bar, parity);
+            bar_wait(bar1, parity);          // layer 1 of this tile is in TMEM (and has finished reading A0)
             tc_fence_after();
             hidden_epilogue(tmem_row, b1, a1, row, col0);
+            if (warp < 4 && more) {          // next tile's observations -> A0, the tile after that -> registers
+                stage_obs();
+                fetch_obs(tile + 2 * (long long)gridDim.x);
+            }
             proxy_fence();
         }
-        parity ^= 1u;
         tc_fence_before();
         __syncthreads();
-        // ---- layer 2: D2[128][256] = A1 . W2^T (16 K steps) ----
+        // ---- layer 2: D2[128][256] = A1 . W2^T (16 K steps), then layer 1 of the next tile behind it ----
         if (warp == kMmaWarp && lane == 0) {
             tc_fence_after();
 #pragma unroll 1
@@ -267,10 +279,11 @@ policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restric
                 umma_bf16(tmem + 256u, umma_desc(sbase + kOffA1 + k * 2 * (kTileM * 16), kTileM * 16, 128),
                           umma_desc(sbase + kOffW2 + k * 2 * (kHidden * 16), kHidden * 16, 128),
                           umma_idesc(kTileM, kHidden), k > 0 ? 1u : 0u);
-            umma_commit(bar);
+            umma_commit(bar2);
+            if (more) issue_layer1();
         }
         if (warp < kMmaWarp) {
-            bar_wait(bar, parity);
+            bar_wait(bar2, parity);
             tc_fence_after();
             // ---- layer-2 epilogue + heads (fp32): rows of w3 are the mean heads, then the std heads ----
             float acc[NH];
@@ -304,7 +317,7 @@ policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restric
         }
         parity ^= 1u;
         tc_fence_before();
-        __syncthreads();   // accumulators, A0, A1 and the partial sums are free for the next tile
+        __syncthreads();   // D2, A1 and the partial sums are free for the next tile
         tc_fence_after();
     }
     if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
