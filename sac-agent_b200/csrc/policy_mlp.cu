@@ -7,14 +7,15 @@
 // The three dense layers are 256 wide.  Through cuBLAS every layer writes its [N][256] activations to HBM
 // and the next one reads them back (1 GB per layer for a million envs); here a CTA keeps a 128-env tile
 // on chip from the observations to the actions:
-//   * all weights (bf16, 144 kB) live in shared memory for the life of the CTA, in the K-major
-//     no-swizzle core-matrix layout the UMMA descriptors address directly;
-//   * the two hidden layers are tcgen05.mma (M = 128 envs, N = 256, K steps of 16) into TMEM; eight epilogue
-//     warps read the accumulators back (tcgen05.ld, one TMEM lane = one env, half a row per thread): after
-//     layer 1 they add the bias, apply ReLU, round to bf16 and write the tile as the A operand of layer 2;
-//     after layer 2 the fp32 activations go straight from registers into the dot products of the two heads
-//     (fp32 weights), the draw and the squash -- the heads never leave the registers;
-//   * the next tile's observations are fetched while the current tile computes;
+//   * all weights (bf16 layers 144 kB + fp32 heads 16 kB) live in shared memory for the life of the CTA, the
+//     bf16 ones in the K-major no-swizzle core-matrix layout the UMMA descriptors address directly;
+//   * the two hidden layers are tcgen05.mma (M = 128 envs, K steps of 16) into TMEM.  An epilogue thread owns
+//     one env row (= one TMEM lane): after layer 1 it reads the accumulator back (tcgen05.ld), adds the bias,
+//     applies ReLU, rounds to bf16 and stores the pairs back into TMEM (tcgen05.st) as the A operand of
+//     layer 2; after layer 2 the fp32 activations go straight from registers into the dot products of the two
+//     heads (fp32 weights), the draw and the squash;
+//   * two tiles are in flight per CTA (two epilogue groups, two TMEM regions), so one tile's epilogue runs
+//     under the other's MMAs; observations are fetched one tile ahead;
 //   * HBM traffic is the input and the output: 4 * obs_dim + 4 * A bytes per env.
 // Inputs are rounded to bf16 (fp32 accumulation): acting only, the learner never sees this kernel.
 #include <cstdint>
@@ -28,8 +29,8 @@
 namespace {
 
 constexpr int kHidden = 256, kTileM = 128, kK1 = 16, kN3 = 16;
-// 8 epilogue warps: warp w works on TMEM lanes 32 (w % 4) .. + 31 (the hardware's lane window of a warp), i.e. on
-// env row 32 (w % 4) + lane, and on the accumulator columns 128 (w / 4) .. + 127 of that row; warp 8 issues the MMAs.
+// 8 epilogue warps in two groups of four (warp w: TMEM lanes 32 (w % 4) .. + 31, the hardware's lane window of a
+// warp; group w / 4); warp 8 issues the MMAs.
 constexpr int kEpiThreads = 256, kThreads = kEpiThreads + 32, kMmaWarp = kEpiThreads / 32;
 // shared-memory map (bytes).  Operand layout: element (row, k) of an R-row operand sits at
 // (k / 8) * (R * 16) + row * 16 + (k % 8) * 2  -- 8x8 core matrices, K-adjacent cores R*16 bytes apart (LBO),
@@ -41,14 +42,7 @@ constexpr int kOffB1 = kOffW3 + kN3 * kHidden * 4;          // fp32[256]
 constexpr int kOffB2 = kOffB1 + kHidden * 4;
 constexpr int kOffB3 = kOffB2 + kHidden * 4;                // fp32[16]
 constexpr int kBlobBytes = kOffB3 + kN3 * 4;                // what the host packs (BOATAGENT_POLICY_BLOB_BYTES)
-constexpr int kOffA0 = (kBlobBytes + 127) / 128 * 128;      // [128 rows][16]
-constexpr int kOffA1 = kOffA0 + kTileM * kK1 * 2;           // [128 rows][256]
-constexpr int kOffPart = kOffA1;                            // fp32 [128 rows][16]: head partial sums of the upper column half
-                                                            // (aliases A1: layer 2 has finished reading it by then)
-constexpr int kOffBar = kOffA1 + kTileM * kHidden * 2;
-constexpr int kSmemBytes = kOffBar + 16;
 static_assert(kBlobBytes == BOATAGENT_POLICY_BLOB_BYTES, "header and kernel disagree on the weight blob");
-static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -115,92 +109,73 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<const uint32_t *>(&p);
 }
 
-// Layer-1 epilogue for the thread's half row (columns col0 .. col0 + 127): accumulator -> + bias -> ReLU -> bf16 ->
-// A operand tile of layer 2.
-__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float *bias, unsigned char *a1, int row, int col0) {
-    uint32_t ra[32], rb[32];
-    tmem_ld32_issue(tmem_row + (uint32_t)col0, ra);
-    auto chunk = [&](const uint32_t (&r)[32], int c) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {   // four 8-column cores
-            const float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 32 + q * 8);
-            const float4 b1 = *reinterpret_cast<const float4 *>(bias + c * 32 + q * 8 + 4);
-            uint4 out;
-            out.x = pack_bf16(fmaxf(__uint_as_float(r[q * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(r[q * 8 + 1]) + b0.y, 0.f));
-            out.y = pack_bf16(fmaxf(__uint_as_float(r[q * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(r[q * 8 + 3]) + b0.w, 0.f));
-            out.z = pack_bf16(fmaxf(__uint_as_float(r[q * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(r[q * 8 + 5]) + b1.y, 0.f));
-            out.w = pack_bf16(fmaxf(__uint_as_float(r[q * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(r[q * 8 + 7]) + b1.w, 0.f));
-            *reinterpret_cast<uint4 *>(a1 + (c * 4 + q) * (kTileM * 16) + row * 16) = out;
-        }
-    };
-    const int c0 = col0 / 32;
-    tmem_ld_wait(ra); tmem_ld32_issue(tmem_row + (uint32_t)(col0 + 32), rb); chunk(ra, c0);
-    tmem_ld_wait(rb); tmem_ld32_issue(tmem_row + (uint32_t)(col0 + 64), ra); chunk(rb, c0 + 1);
-    tmem_ld_wait(ra); tmem_ld32_issue(tmem_row + (uint32_t)(col0 + 96), rb); chunk(ra, c0 + 2);
-    tmem_ld_wait(rb); chunk(rb, c0 + 3);
+// Two tiles in flight per CTA.  Epilogue group g (warps 4g .. 4g + 3, one env row = one TMEM lane per thread) owns
+// the TMEM columns 256 g .. 256 g + 255 and every other tile of the CTA.  The layer-1 activations never go to
+// shared memory: the epilogue packs them to bf16 pairs and stores them back into TMEM (tcgen05.st, in place over
+// the accumulator columns it has already read), and layer 2 takes its A operand from TMEM.  Layer 2 runs as two
+// N = 128 halves into the upper 128 columns of the region, so while one group is in an epilogue the tensor pipe
+// works for the other.  Hand-offs are mbarriers (no CTA-wide barrier in the loop); the MMA warp polls them.
+constexpr int kOffA0 = (kBlobBytes + 127) / 128 * 128;      // two [128 rows][16] tiles
+constexpr int kOffBar = kOffA0 + 2 * kTileM * kK1 * 2;      // 2 groups x {a0_ready, d1_ready, h1_ready, d2_ready, d2_free}
+constexpr int kSmemBytes = kOffBar + 2 * 5 * 8;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+enum { B_A0 = 0, B_D1 = 1, B_H1 = 2, B_D2 = 3, B_FREE = 4 };
+
+__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool bar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// D[tmem] (+)= A[tmem, bf16 pairs per column] . B[smem]^T
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+        "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
 }
 
-// Layer-2 epilogue fused with the two heads: h2 = relu(acc + bias) stays in fp32 registers and goes straight into
-// the 2 * n_actions dot products with the fp32 head weights (shared memory, broadcast reads).  acc[j] += partial sums
-// over this thread's 128 columns.
-template <int NH>
-__device__ __forceinline__ void heads_epilogue(uint32_t tmem_row, const float *bias, const float *w3, int col0, float (&acc)[NH]) {
-#pragma unroll
-    for (int j = 0; j < NH; ++j) acc[j] = 0.f;
-    uint32_t ra[32], rb[32];
-    tmem_ld32_issue(tmem_row + (uint32_t)col0, ra);
-    auto chunk = [&](const uint32_t (&r)[32], int c) {
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 b = *reinterpret_cast<const float4 *>(bias + c * 32 + 4 * i);
-            v[4 * i + 0] = fmaxf(__uint_as_float(r[4 * i + 0]) + b.x, 0.f);
-            v[4 * i + 1] = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
-            v[4 * i + 2] = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f);
-            v[4 * i + 3] = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
-        }
-#pragma unroll
-        for (int j = 0; j < NH; ++j) {
-            const float4 *w = reinterpret_cast<const float4 *>(w3 + j * kHidden + c * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 ww = w[i];
-                acc[j] = fmaf(v[4 * i + 0], ww.x, acc[j]);
-                acc[j] = fmaf(v[4 * i + 1], ww.y, acc[j]);
-                acc[j] = fmaf(v[4 * i + 2], ww.z, acc[j]);
-                acc[j] = fmaf(v[4 * i + 3], ww.w, acc[j]);
-            }
-        }
-    };
-    const int c0 = col0 / 32;
-    tmem_ld_wait(ra); tmem_ld32_issue(tmem_row + (uint32_t)(col0 + 32), rb); chunk(ra, c0);
-    tmem_ld_wait(rb); tmem_ld32_issue(tmem_row + (uint32_t)(col0 + 64), ra); chunk(rb, c0 + 1);
-    tmem_ld_wait(ra); tmem_ld32_issue(tmem_row + (uint32_t)(col0 + 96), rb); chunk(ra, c0 + 2);
-    tmem_ld_wait(rb); chunk(rb, c0 + 3);
-}
-
-template <int NA>   // NA = n_actions (1, 2, 4 or 8 instantiated)
+template <int NA>
 __global__ void __launch_bounds__(kThreads, 1)
 policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restrict__ obs, const float *__restrict__ eps,
-                  const float *__restrict__ max_action, unsigned long long seed, unsigned long long step, long long n,
-                  int obs_dim, float *__restrict__ action_out) {
+                   const float *__restrict__ max_action, unsigned long long seed, unsigned long long step, long long n,
+                   int obs_dim, float *__restrict__ action_out) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t tmem_base_slot;
     constexpr int NH = 2 * NA;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row = (warp & 3) * 32 + lane;      // env row of the tile this epilogue thread works on
-    const int col0 = (warp >> 2) * 128;          // its half of the accumulator columns (epilogue warps only)
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kOffBar);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
 
-    // ---- one-time setup: weights into shared memory, barrier, TMEM ----
     for (int i = tid; i < kBlobBytes / 16; i += kThreads)
         reinterpret_cast<uint4 *>(smem)[i] = __ldg(reinterpret_cast<const uint4 *>(blob) + i);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar + 1)) : "memory");
+        for (int g = 0; g < 2; ++g) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_addr(bars + 5 * g + B_A0)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars + 5 * g + B_D1)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_addr(bars + 5 * g + B_H1)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars + 5 * g + B_D2)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_addr(bars + 5 * g + B_FREE)) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kMmaWarp) {   // the MMA warp owns the 512 TMEM columns (two 128 x 256 fp32 accumulators)
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -209,96 +184,158 @@ policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restric
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp & 3) * 32u << 16);
     const uint32_t sbase = smem_addr(smem);
-    const float *b1 = reinterpret_cast<const float *>(smem + kOffB1), *b2 = reinterpret_cast<const float *>(smem + kOffB2),
-                *b3 = reinterpret_cast<const float *>(smem + kOffB3), *w3 = reinterpret_cast<const float *>(smem + kOffW3);
-    unsigned char *a0 = smem + kOffA0, *a1 = smem + kOffA1;
-    float *part = reinterpret_cast<float *>(smem + kOffPart);
-    uint32_t parity = 0;
-
     const long long n_tiles = (n + kTileM - 1) / kTileM;
-    uint64_t *bar1 = bar, *bar2 = bar + 1;   // layer-1 / layer-2 accumulator ready
-    // Software pipeline over the CTA's tiles: layer 1 of tile t + 1 is issued right behind layer 2 of tile t, so it
-    // (and the staging of its observations) runs under the layer-2 epilogue of tile t; the observation rows are
-    // fetched from HBM one more tile ahead (warps 0-3: one row each).
-    float o[kK1];
-    auto fetch_obs = [&](long long t) {
-        const long long e = t * kTileM + row;
+    const long long G = gridDim.x;
+    // local tile j of this CTA is global tile blockIdx.x + j * G; group g takes the local tiles j = 2 i + g
+    const long long my_tiles = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + G - 1) / G : 0;
+
+    if (warp == kMmaWarp) {
+        if (lane == 0) {
+            // ===== MMA issuer: a small state machine per group, served in whatever order the barriers complete =====
+            int state[2] = {0, 0};
+            long long it[2] = {0, 0};
+            const long long cnt[2] = {(my_tiles + 1) / 2, my_tiles / 2};
+            while (it[0] < cnt[0] || it[1] < cnt[1]) {
 #pragma unroll
-        for (int q = 0; q < kK1; ++q) o[q] = (q < obs_dim && t < n_tiles && e < n) ? __ldg(obs + e * obs_dim + q) : 0.f;
-    };
-    auto stage_obs = [&]() {   // registers -> bf16 A0 [128][16]
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            uint4 out;
-            out.x = pack_bf16(o[j * 8 + 0], o[j * 8 + 1]);
-            out.y = pack_bf16(o[j * 8 + 2], o[j * 8 + 3]);
-            out.z = pack_bf16(o[j * 8 + 4], o[j * 8 + 5]);
-            out.w = pack_bf16(o[j * 8 + 6], o[j * 8 + 7]);
-            *reinterpret_cast<uint4 *>(a0 + j * (kTileM * 16) + row * 16) = out;
+                for (int g = 0; g < 2; ++g) {
+                    if (it[g] >= cnt[g]) continue;
+                    uint64_t *b = bars + 5 * g;
+                    const uint32_t par = (uint32_t)(it[g] & 1);
+                    const uint32_t region = tmem + 256u * g;
+                    if (state[g] == 0) {          // observations staged -> layer 1: D1[128][256] = A0 . W1^T
+                        if (!bar_test(b + B_A0, par)) continue;
+                        tc_fence_after();
+                        umma_bf16(region, umma_desc(sbase + kOffA0 + g * (kTileM * kK1 * 2), kTileM * 16, 128),
+                                  umma_desc(sbase + kOffW1, kHidden * 16, 128), umma_idesc(kTileM, kHidden), 0u);
+                        umma_commit(b + B_D1);
+                        state[g] = 1;
+                    } else {                      // h1 is in TMEM (state 1) / the first half has been read (state 2)
+                        if (!bar_test(b + (state[g] == 1 ? B_H1 : B_FREE), par)) continue;
+                        tc_fence_after();
+                        const int half = state[g] - 1;   // output columns 128 half .. + 127 of layer 2
+#pragma unroll 1
+                        for (int k = 0; k < kHidden / 16; ++k)
+                            umma_bf16_ts(region + 128u, region + 8u * k,
+                                         umma_desc(sbase + kOffW2 + half * (128 * 16) + k * 2 * (kHidden * 16), kHidden * 16, 128),
+                                         umma_idesc(kTileM, 128), k > 0 ? 1u : 0u);
+                        umma_commit(b + B_D2);
+                        if (state[g] == 1) state[g] = 2;
+                        else { state[g] = 0; ++it[g]; }
+                    }
+                }
+            }
         }
-    };
-    auto issue_layer1 = [&]() {   // D1[128][256] = A0 . W1^T (one K step)
-        umma_bf16(tmem, umma_desc(sbase + kOffA0, kTileM * 16, 128), umma_desc(sbase + kOffW1, kHidden * 16, 128),
-                  umma_idesc(kTileM, kHidden), 0u);
-        umma_commit(bar1);
-    };
-    if (warp < 4) {
-        fetch_obs(blockIdx.x);
-        stage_obs();
-        proxy_fence();
-        fetch_obs((long long)blockIdx.x + gridDim.x);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == kMmaWarp && lane == 0) {
-        tc_fence_after();
-        issue_layer1();
-    }
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long env = tile * kTileM + row;
-        const bool more = tile + gridDim.x < n_tiles;
-        if (warp < kMmaWarp) {
-            bar_wait(bar1, parity);          // layer 1 of this tile is in TMEM (and has finished reading A0)
-            tc_fence_after();
-            hidden_epilogue(tmem_row, b1, a1, row, col0);
-            if (warp < 4 && more) {          // next tile's observations -> A0, the tile after that -> registers
-                stage_obs();
-                fetch_obs(tile + 2 * (long long)gridDim.x);
+    } else {
+        // ===== epilogue group g: one env row per thread =====
+        const int g = warp >> 2, row = (warp & 3) * 32 + lane;
+        uint64_t *b = bars + 5 * g;
+        const uint32_t region = tmem + 256u * g + ((uint32_t)(warp & 3) * 32u << 16);
+        const float *b1 = reinterpret_cast<const float *>(smem + kOffB1), *b2 = reinterpret_cast<const float *>(smem + kOffB2),
+                    *b3 = reinterpret_cast<const float *>(smem + kOffB3), *w3 = reinterpret_cast<const float *>(smem + kOffW3);
+        unsigned char *a0 = smem + kOffA0 + g * (kTileM * kK1 * 2);
+        const long long cnt = g == 0 ? (my_tiles + 1) / 2 : my_tiles / 2;
+        float o[kK1];
+        auto fetch_obs = [&](long long i) {
+            const long long e = ((long long)blockIdx.x + (2 * i + g) * G) * kTileM + row;
+#pragma unroll
+            for (int q = 0; q < kK1; ++q) o[q] = (q < obs_dim && i < cnt && e < n) ? __ldg(obs + e * obs_dim + q) : 0.f;
+        };
+        fetch_obs(0);
+        for (long long i = 0; i < cnt; ++i) {
+            const long long env = ((long long)blockIdx.x + (2 * i + g) * G) * kTileM + row;
+            const uint32_t par = (uint32_t)(i & 1);
+            // ---- observations -> bf16 A0 (the previous tile's epilogue, i.e. every read of this region, is behind us) ----
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint4 out;
+                out.x = pack_bf16(o[j * 8 + 0], o[j * 8 + 1]);
+                out.y = pack_bf16(o[j * 8 + 2], o[j * 8 + 3]);
+                out.z = pack_bf16(o[j * 8 + 4], o[j * 8 + 5]);
+                out.w = pack_bf16(o[j * 8 + 6], o[j * 8 + 7]);
+                *reinterpret_cast<uint4 *>(a0 + j * (kTileM * 16) + row * 16) = out;
             }
             proxy_fence();
-        }
-        tc_fence_before();
-        __syncthreads();
-        // ---- layer 2: D2[128][256] = A1 . W2^T (16 K steps), then layer 1 of the next tile behind it ----
-        if (warp == kMmaWarp && lane == 0) {
+            tc_fence_before();
+            bar_arrive(b + B_A0);
+            fetch_obs(i + 1);
+            // ---- layer-1 epilogue: accumulator -> + bias -> ReLU -> bf16 pairs, back into TMEM in place ----
+            bar_wait(b + B_D1, par);
             tc_fence_after();
-#pragma unroll 1
-            for (int k = 0; k < kHidden / 16; ++k)
-                umma_bf16(tmem + 256u, umma_desc(sbase + kOffA1 + k * 2 * (kTileM * 16), kTileM * 16, 128),
-                          umma_desc(sbase + kOffW2 + k * 2 * (kHidden * 16), kHidden * 16, 128),
-                          umma_idesc(kTileM, kHidden), k > 0 ? 1u : 0u);
-            umma_commit(bar2);
-            if (more) issue_layer1();
-        }
-        if (warp < kMmaWarp) {
-            bar_wait(bar2, parity);
-            tc_fence_after();
-            // ---- layer-2 epilogue + heads (fp32): rows of w3 are the mean heads, then the std heads ----
-            float acc[NH];
-            heads_epilogue<NH>(tmem_row + 256u, b2, w3, col0, acc);
-            if (col0 != 0) {
+            {
+                uint32_t ra[32], rb[32];
+                auto chunk = [&](const uint32_t (&r)[32], int c) {
+                    uint32_t packed[16];
 #pragma unroll
-                for (int j = 0; j < NH; ++j) part[row * kN3 + j] = acc[j];
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(b1 + c * 32 + 4 * q);
+                        packed[2 * q] = pack_bf16(fmaxf(__uint_as_float(r[4 * q + 0]) + bb.x, 0.f),
+                                                  fmaxf(__uint_as_float(r[4 * q + 1]) + bb.y, 0.f));
+                        packed[2 * q + 1] = pack_bf16(fmaxf(__uint_as_float(r[4 * q + 2]) + bb.z, 0.f),
+                                                      fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f));
+                    }
+                    tmem_st16(region + 16u * c, packed);   // columns 16 c .. 16 c + 15 <= what has been read so far
+                };
+                tmem_ld32_issue(region, ra);
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    tmem_ld_wait(ra); tmem_ld32_issue(region + 32u * (c + 1), rb); chunk(ra, c);
+                    tmem_ld_wait(rb);
+                    if (c + 2 < 8) tmem_ld32_issue(region + 32u * (c + 2), ra);
+                    chunk(rb, c + 1);
+                }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
-            if (col0 == 0 && env < n) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            bar_arrive(b + B_H1);
+            // ---- layer-2 epilogue (two halves of 128 columns) fused with the fp32 heads ----
+            float acc[NH];
+#pragma unroll
+            for (int j = 0; j < NH; ++j) acc[j] = 0.f;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                bar_wait(b + B_D2, (uint32_t)half);   // two completions per tile: parities 0, 1
+                tc_fence_after();
+                uint32_t ra[32], rb[32];
+                auto chunk = [&](const uint32_t (&r)[32], int c) {   // c: 32-column chunk of the 256 layer-2 outputs
+                    float v[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(b2 + c * 32 + 4 * q);
+                        v[4 * q + 0] = fmaxf(__uint_as_float(r[4 * q + 0]) + bb.x, 0.f);
+                        v[4 * q + 1] = fmaxf(__uint_as_float(r[4 * q + 1]) + bb.y, 0.f);
+                        v[4 * q + 2] = fmaxf(__uint_as_float(r[4 * q + 2]) + bb.z, 0.f);
+                        v[4 * q + 3] = fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NH; ++j) {
+                        const float4 *w = reinterpret_cast<const float4 *>(w3 + j * kHidden + c * 32);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 ww = w[q];
+                            acc[j] = fmaf(v[4 * q + 0], ww.x, acc[j]);
+                            acc[j] = fmaf(v[4 * q + 1], ww.y, acc[j]);
+                            acc[j] = fmaf(v[4 * q + 2], ww.z, acc[j]);
+                            acc[j] = fmaf(v[4 * q + 3], ww.w, acc[j]);
+                        }
+                    }
+                };
+                const uint32_t d2 = region + 128u;
+                tmem_ld32_issue(d2, ra);
+                tmem_ld_wait(ra); tmem_ld32_issue(d2 + 32u, rb); chunk(ra, half * 4 + 0);
+                tmem_ld_wait(rb); tmem_ld32_issue(d2 + 64u, ra); chunk(rb, half * 4 + 1);
+                tmem_ld_wait(ra); tmem_ld32_issue(d2 + 96u, rb); chunk(ra, half * 4 + 2);
+                tmem_ld_wait(rb); chunk(rb, half * 4 + 3);
+                if (half == 0) {   // the columns may be overwritten by the second half now
+                    tc_fence_before();
+                    bar_arrive(b + B_FREE);
+                }
+            }
+            if (env < n) {
 #pragma unroll
                 for (int a = 0; a < NA; ++a) {   // sample_normal, networks.py:47-65
-                    const float mean = acc[a] + part[row * kN3 + a] + b3[a];
-                    const float raw = acc[NA + a] + part[row * kN3 + NA + a] + b3[NA + a];
-                    const float log_std = -5.0f + 3.5f * (tanhf(raw) + 1.0f);
+                    const float mean = acc[a] + b3[a];
+                    const float log_std = -5.0f + 3.5f * (tanhf(acc[NA + a] + b3[NA + a]) + 1.0f);
                     float e;
                     if (eps) {
                         e = __ldg(eps + env * NA + a);
@@ -315,11 +352,9 @@ policy_mlp_kernel(const unsigned char *__restrict__ blob, const float *__restric
                 }
             }
         }
-        parity ^= 1u;
-        tc_fence_before();
-        __syncthreads();   // D2, A1 and the partial sums are free for the next tile
-        tc_fence_after();
     }
+    tc_fence_before();
+    __syncthreads();
     if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
