@@ -91,8 +91,13 @@ class SACLearner:
     """The five networks, their Adam optimisers and one SAC-v1 update (continuous_agent.py:96-154)."""
 
     def __init__(self, input_dims, n_actions, max_action, alpha, beta, gamma, tau, reward_scale, experiment_dir=None,
-                 device="cuda"):
+                 device="cuda", torch_reference_math=False):
         self.device = torch.device(device)
+        if self.device.type != "cuda" and not torch_reference_math:
+            # no silent CPU fallback: off the GPU the head and the optimiser are plain PyTorch (the restatement
+            # the parity tests compare the reference's learn() with), and that has to be asked for
+            raise RuntimeError("SACLearner needs a CUDA device; pass torch_reference_math=True for the PyTorch "
+                               "restatement of the update (parity tests only)")
         self.gamma, self.tau, self.scale = float(gamma), float(tau), float(reward_scale)
         d = tuple(input_dims)
         # creation order = the reference's (continuous_agent.py:19-52): identical torch seeds give identical weights

@@ -29,7 +29,7 @@ def _learner(meta, device):
     L = SACLearner((11,), 1, np.array([1.0], dtype=np.float32), float(meta["meta/learning_rate_alpha"]),
                    float(meta["meta/learning_rate_beta"]), float(meta["meta/gamma"]),
                    float(meta["meta/tvn_parameter_modulation_tau"]), float(meta["meta/reward_scale"]),
-                   device=device)
+                   device=device, torch_reference_math=(device == "cpu"))
     return L
 
 
@@ -117,8 +117,10 @@ def test_learner_cpu_matches_live_reference_on_a_fresh_seed():
 
 
 def test_agent_needs_cuda():
+    with pytest.raises(RuntimeError):   # the learner does not fall back to the CPU on its own
+        SACLearner((11,), 1, np.array([1.0], dtype=np.float32), 5e-3, 3e-4, 0.99, 0.005, 10, device="cpu")
     if torch.cuda.is_available():
-        pytest.skip("CUDA present")
+        return
     env = type("E", (), {"action_space": S.Box(low=-1, high=1, dtype=np.float32)})()
     with pytest.raises(RuntimeError):
         ContinuousAgent(S.load_config(), None, (11,), env)
