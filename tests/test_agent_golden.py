@@ -342,3 +342,28 @@ def test_reduced_precision_acting_stays_close_to_fp32(precision, tol):
     with pytest.raises(ValueError):
         ContinuousAgent(cfg, None, (11,), env, device=0, memory=mem, policy_precision="fp8")
     mem.close()
+
+
+@pytest.mark.gpu
+def test_agent_kernel_argument_errors():
+    """The agent entry points of the ABI reject bad arguments with codes instead of launching."""
+    from sac_agent_b200 import _lib
+    from sac_agent_b200.continuous_agent import DeviceAdam
+    from sac_agent_b200.networks import ActorNetwork, TensorCorePolicy
+    L = _lib.lib()
+    x = torch.zeros(8, device="cuda")
+    assert L.boatagent_policy_act(None, x.data_ptr(), None, x.data_ptr(), 0, 0, 8, 11, 1, x.data_ptr(), None) != 0
+    assert L.boatagent_policy_act(x.data_ptr(), x.data_ptr(), None, x.data_ptr(), 0, 0, 0, 11, 1, x.data_ptr(), None) != 0
+    assert L.boatagent_policy_act(x.data_ptr(), x.data_ptr(), None, x.data_ptr(), 0, 0, 8, 17, 1, x.data_ptr(), None) != 0
+    assert L.boatagent_policy_act(x.data_ptr(), x.data_ptr(), None, x.data_ptr(), 0, 0, 8, 11, 3, x.data_ptr(), None) != 0
+    assert L.boatagent_gaussian_head_forward(None, None, None, None, 4, 1, None, None, None) != 0
+    assert L.boatagent_adam_polyak_step(None, 1, 0.9, 0.999, 1e-8, 0.0, x.data_ptr(), None) != 0
+    with pytest.raises(ValueError):
+        DeviceAdam([([torch.zeros(4, device="cuda") for _ in range(65)], 1e-3)])
+    with pytest.raises(ValueError):
+        DeviceAdam([([torch.zeros(4, device="cuda", dtype=torch.float64)], 1e-3)])
+    with pytest.raises(ValueError):   # three actions: not one of the instantiated head counts
+        TensorCorePolicy(ActorNetwork(None, (11,), np.ones(3, dtype=np.float32), n_actions=3).cuda())
+    pol = TensorCorePolicy(ActorNetwork(None, (11,), np.ones(1, dtype=np.float32), n_actions=1).cuda())
+    with pytest.raises(ValueError):
+        pol.act(torch.zeros(4, 12, device="cuda"))

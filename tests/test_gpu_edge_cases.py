@@ -229,3 +229,35 @@ def test_single_env_step_latency(S):
     assert per_step < 0.2e-3 and per_step_rec < 0.4e-3
     assert d["boat_position_x"] > 0 and d["n"] == 20
     env.close()
+
+
+def test_env_state_host_and_zero_copy_errors(S):
+    """boatenv_env_state_host: all ten fields of one env in one call, equal to the per-field reads; argument and
+    state errors come back as codes (re-raised by the binding), never as a crash."""
+    import ctypes as C
+    cfg = S.load_config(base_settings__experiment=4)
+    env = S.BatchedBoatEnv(cfg, 100, seed=2, precision="fp64", device=0, auto_reset=True)
+    out = (C.c_double * 10)()
+    assert env._L.boatenv_env_state_host(env._h, 0, out) != 0   # before reset: BOATENV_ESTATE
+    env.reset()
+    for t in range(7):
+        env.step(env.uniform_actions(t, 0.5))
+    for i in (0, 31, 32, 99):
+        assert env._L.boatenv_env_state_host(env._h, i, out) == 0
+        for name, f in S.boat_env.FIELDS.items():
+            assert float(env.get_field(name)[i].item()) == out[f], (i, name)
+    assert env._L.boatenv_env_state_host(env._h, 100, out) != 0 and env._L.boatenv_env_state_host(env._h, -1, out) != 0
+    assert env._L.boatenv_env_state_host(env._h, 0, None) != 0
+    # zero-copy host step in fp64 at the size limit, against the device step of a twin
+    twin = S.BatchedBoatEnv(cfg, 100, seed=2, precision="fp64", device=0, auto_reset=True)
+    twin.reset()
+    for t in range(7):
+        twin.step(twin.uniform_actions(t, 0.5))
+    acts = env.uniform_actions(7, 0.5)
+    o, r, d, _ = twin.step(acts)
+    ah, oh = acts.cpu().numpy().copy(), np.empty((100, 11))
+    rh, dh = np.empty(100), np.empty(100, dtype=np.uint8)
+    rc = env._L.boatenv_step_host(env._h, ah.ctypes.data, oh.ctypes.data, rh.ctypes.data, dh.ctypes.data, 1)
+    assert rc == 0 and np.array_equal(oh, o.cpu().numpy()) and np.array_equal(rh, r.cpu().numpy())
+    assert np.array_equal(dh, d.cpu().numpy())
+    env.close(); twin.close()
