@@ -268,12 +268,13 @@ int boatenv_create(const boatenv_params *params, int64_t n_envs, uint64_t seed, 
     cfg.seed = seed;
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
-    {   // tile-blocked state: [dyn][idx][wind A][wind B] sections per 32-env block (common.cuh)
+    {   // tile-blocked state: [dyn][step index][wind A][wind B][episode] sections per 32-env block (common.cuh)
         const int nd = D_COUNT * (int)h->esize / 16, nw = 4 * (int)h->esize / 16;
         cfg.off_idx = 32 * 16 * nd;
-        cfg.off_wa = cfg.off_idx + 32 * 8;
+        cfg.off_wa = cfg.off_idx + 32 * 4;
         cfg.off_wb = cfg.off_wa + (cfg.ncurves >= 1 ? 32 * 16 * nw : 0);
-        cfg.block_bytes = cfg.off_wb + (cfg.ncurves >= 2 ? 32 * 16 * nw : 0);
+        cfg.off_epi = cfg.off_wb + (cfg.ncurves >= 2 ? 32 * 16 * nw : 0);
+        cfg.block_bytes = cfg.off_epi + 32 * 4;
     }
     const size_t state_bytes = (size_t)num_blocks(n_envs) * (size_t)cfg.block_bytes;
     alloc((void **)&cfg.state, state_bytes);

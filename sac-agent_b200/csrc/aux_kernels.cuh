@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(kTile) boat_reset_kernel(const __grid_constant
     const bool active = i < c.n_envs;
     const bool want = active && (mask == nullptr || mask[i] != 0);
     uint32_t episode = 0;
-    if (want) episode = reinterpret_cast<const uint2 *>(block_section(c, i, c.off_idx))[lane].y + 1u;
+    if (want) episode = *episode_ptr(c, i) + 1u;
     // experiments 1-3 draw no wind curves: nothing is warp-cooperative, every lane resets its own env at once
     unsigned todo = c.ncurves > 0 ? __ballot_sync(FULL, want) : (want ? 1u : 0u);
     while (todo) {
@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(kTile) boat_reset_kernel(const __grid_constant
                 wb[m] = c.ncurves > 0 ? (T)scratch_s[warp][4 + m] : (T)0;
             }
             store_vecs<T, D_COUNT>(block_section(c, i, 0), lane, d);
-            reinterpret_cast<uint2 *>(block_section(c, i, c.off_idx))[lane] = make_uint2(0u, e_epi);
+            *index_ptr(c, i) = 0u;
+            *episode_ptr(c, i) = e_epi;
             if (c.ncurves >= 1) store_vecs<T, 4>(block_section(c, i, c.off_wa), lane, wa);
             if (c.ncurves >= 2) store_vecs<T, 4>(block_section(c, i, c.off_wb), lane, wb);
             if (obs_out) {
@@ -94,7 +95,7 @@ static __global__ void __launch_bounds__(32) boat_wind_table_kernel(const __grid
     __shared__ double folded[kMaxKnots - 1][8];
     const int lane = threadIdx.x;
     const double PI = 3.14159265358979323846;
-    const uint32_t episode = reinterpret_cast<const uint2 *>(block_section(c, env, c.off_idx))[env & 31].y;
+    const uint32_t episode = *episode_ptr(c, env);
     if (c.ncurves > 0) {
         for (int j = 0; j < c.npieces; ++j) {
             const int first_index = (j * c.Lm1 + c.npieces - 1) / c.npieces;
@@ -141,8 +142,7 @@ __global__ void boat_get_field_kernel(const __grid_constant__ DevCfg c, int fiel
     if (field < D_COUNT) {
         reinterpret_cast<T *>(out)[i] = *dyn_scalar<T>(c, i, field);
     } else {
-        const uint2 v = reinterpret_cast<const uint2 *>(block_section(c, i, c.off_idx))[i & 31];
-        reinterpret_cast<uint32_t *>(out)[i] = (field == BOATENV_F_STEP_INDEX) ? v.x : v.y;
+        reinterpret_cast<uint32_t *>(out)[i] = (field == BOATENV_F_STEP_INDEX) ? *index_ptr(c, i) : *episode_ptr(c, i);
     }
 }
 
@@ -153,11 +153,8 @@ __global__ void boat_set_field_kernel(const __grid_constant__ DevCfg c, int fiel
     if (field < D_COUNT) {
         *dyn_scalar<T>(c, i, field) = reinterpret_cast<const T *>(in)[i];
     } else {
-        uint2 *p = reinterpret_cast<uint2 *>(block_section(c, i, c.off_idx)) + (i & 31);
-        uint2 v = *p;
         const uint32_t x = reinterpret_cast<const uint32_t *>(in)[i];
-        if (field == BOATENV_F_STEP_INDEX) v.x = x; else v.y = x;
-        *p = v;
+        if (field == BOATENV_F_STEP_INDEX) *index_ptr(c, i) = x; else *episode_ptr(c, i) = x;
     }
 }
 
@@ -168,9 +165,8 @@ __global__ void boat_env_state_kernel(const __grid_constant__ DevCfg c, long lon
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
 #pragma unroll
     for (int f = 0; f < D_COUNT; ++f) out[f] = (double)*dyn_scalar<T>(c, i, f);
-    const uint2 v = reinterpret_cast<const uint2 *>(block_section(c, i, c.off_idx))[i & 31];
-    out[BOATENV_F_STEP_INDEX] = (double)v.x;
-    out[BOATENV_F_EPISODE] = (double)v.y;
+    out[BOATENV_F_STEP_INDEX] = (double)*index_ptr(c, i);
+    out[BOATENV_F_EPISODE] = (double)*episode_ptr(c, i);
 }
 
 // counters[kCounterSlots][32 doubles, first 8 used] -> out[8]

@@ -507,8 +507,8 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
         for (int s = 0; s < kStages; ++s) {
             const int q = seq + s * wstride;
             if (q < blk_end) {
-                mbar_expect_tx(full + s, (uint32_t)bb);
-                tma_load_1d(stage_base + s * bb, c.state + (size_t)block_of(q) * (size_t)bb, (uint32_t)bb, full + s);
+                mbar_expect_tx(full + s, (uint32_t)c.off_epi);   // everything but the episode row
+                tma_load_1d(stage_base + s * bb, c.state + (size_t)block_of(q) * (size_t)bb, (uint32_t)c.off_epi, full + s);
             }
         }
         if (fused_store) prev_prefetch(seq, 0);
@@ -539,18 +539,17 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
         load_vecs<T, D_COUNT>(reinterpret_cast<const char *>(sb), lane, d);
         if (kCurves) load_vecs<T, 4>(reinterpret_cast<const char *>(sb) + c.off_wa, lane, wa);
         if (WK == WIND_BOTH) load_vecs<T, 4>(reinterpret_cast<const char *>(sb) + c.off_wb, lane, wb);
-        const uint2 ix = reinterpret_cast<const uint2 *>(sb + c.off_idx)[lane];  // last LDS of the stage
-        int index = (int)ix.x;
-        uint32_t episode = ix.y;
+        const uint32_t ixw = reinterpret_cast<const uint32_t *>(sb + c.off_idx)[lane];  // last LDS of the stage
+        int index = (int)ixw;
         __syncwarp();
         if (lane == 0) {
             // The stage is consumed: refill it kStages blocks ahead.  The block number carries a data
             // dependency on the LAST shared-memory load of the stage (bit 31 of the step index is never
             // set), so the bulk copy cannot be issued before the warp's loads have returned.
-            const int q = seq + kStages * wstride + (int)(ix.x >> 31);
+            const int q = seq + kStages * wstride + (int)(ixw >> 31);
             if (q < blk_end) {
-                mbar_expect_tx(full + stage, (uint32_t)bb);
-                tma_load_1d(stage_base + stage * bb, c.state + (size_t)block_of(q) * (size_t)bb, (uint32_t)bb, full + stage);
+                mbar_expect_tx(full + stage, (uint32_t)c.off_epi);
+                tma_load_1d(stage_base + stage * bb, c.state + (size_t)block_of(q) * (size_t)bb, (uint32_t)c.off_epi, full + stage);
             }
         }
         if (++stage == kStages) { stage = 0; parity ^= 1u; }
@@ -572,7 +571,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             if (active) {
 #ifndef BOAT_DEBUG_SKIP_STATE
                 store_vecs<T, D_COUNT>(gb, lane, d);
-                st_state(reinterpret_cast<uint2 *>(gb + c.off_idx) + lane, make_uint2((uint32_t)index, episode));
+                st_state(reinterpret_cast<uint32_t *>(gb + c.off_idx) + lane, (uint32_t)index);
 #endif
                 if (KMULTI && wind_dirty) {  // wind coefficients change only on the slow path
                     if (kCurves) store_vecs<T, 4>(gb + c.off_wa, lane, wa);
@@ -695,6 +694,10 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                     ring_in_flight = false;
                 }
                 const bool is_done = need_setup && active && code != BOATENV_TERM_NONE;
+                // the episode number lives outside the streamed part of the block: fetched only here, written only
+                // when an episode ends
+                uint32_t *epi_g = reinterpret_cast<uint32_t *>(gb + c.off_epi) + lane;
+                uint32_t episode = (need_setup && active) ? *epi_g : 0u;
                 if (is_done) {  // statistics (info dict, boat_env.py:24-32,87-113): sparse events -> per-env REDs
                     double *cnt = c.counters + (blk & (kCounterSlots - 1)) * 32;
                     const double ret = (double)d[D_RET];
@@ -727,7 +730,8 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                             for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
                             stage_reset_obs<T>(c, row, (T)0);  // only experiment 2 starts off the centre line (:166-167)
                             store_vecs<T, D_COUNT>(gb, lane, d);
-                            st_state(reinterpret_cast<uint2 *>(gb + c.off_idx) + lane, make_uint2(0u, rq.episode));
+                            st_state(reinterpret_cast<uint32_t *>(gb + c.off_idx) + lane, 0u);
+                            *epi_g = rq.episode;
                         }
                     }
                 }
@@ -742,6 +746,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                     for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
                     index = 0;
                     episode += 1u;
+                    *epi_g = episode;
                     wind_dirty = false;  // the old episode's coefficients are dead; the follow-up kernel writes the new ones
                     stage_reset_obs<T>(c, row, (T)0);  // only experiment 2 starts off the centre line (:166-167)
                     deferred = true;
@@ -775,10 +780,11 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                             d[D_SY] = sy0;
                             index = 0;
                             episode = e_epi;
+                            *epi_g = e_epi;
                             stage_reset_obs<T>(c, row, sy0);
                             if (!KMULTI) {
                                 store_vecs<T, D_COUNT>(gb, lane, d);
-                                st_state(reinterpret_cast<uint2 *>(gb + c.off_idx) + lane, make_uint2(0u, e_epi));
+                                st_state(reinterpret_cast<uint32_t *>(gb + c.off_idx) + lane, 0u);
                             }
                         }
                     }

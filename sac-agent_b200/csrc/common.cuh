@@ -3,11 +3,13 @@
 // State layout in HBM (DESIGN.md "data layout"): tile-blocked structure-of-arrays.  The
 // carried state of 32 consecutive envs (one warp's tile) is ONE contiguous, 16-byte
 // aligned block
-//     [dyn vector 0 x 32][dyn vector 1 x 32]..[idx (uint2) x 32][wind A vectors x 32][wind B vectors x 32]
+//     [dyn vector 0 x 32][dyn vector 1 x 32]..[step index (u32) x 32][wind A vectors x 32][wind B vectors x 32][episode (u32) x 32]
 // of 16-byte vectors (VW = 16/sizeof(T) scalars each), so that
-//   * the whole block is fetched by a single TMA bulk copy (cp.async.bulk) into shared memory,
+//   * everything a step reads is fetched by a single TMA bulk copy (cp.async.bulk) into shared memory,
 //   * a warp's access to one vector row is one fully coalesced 512-byte LDS/LDG/STG.128.
-// Block size: 32 * (16*ND + 8 + 16*NW*ncurves) bytes = 1280 / 1792 / 2304 (fp32; exp 1-3 / 4-5 / 6).
+// The episode number sits at the END of the block, outside the bulk copy: only a reset reads or writes it, so it
+// costs no HBM traffic on the common path (it used to travel with the step index: 8 bytes per env-step).
+// Block size: 32 * (16*ND + 4 + 16*NW*ncurves + 4) bytes = 1280 / 1792 / 2304 (fp32; exp 1-3 / 4-5 / 6).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -75,7 +77,8 @@ struct DevCfg {
     // device buffers (owned by the handle)
     char *state;              // [ceil(n_envs / 32)][block_bytes] tile-blocked state (see top of file)
     int block_bytes;          // bytes of one 32-env block
-    int off_idx, off_wa, off_wb;  // byte offsets of the idx / wind A / wind B sections inside a block
+    int off_idx, off_wa, off_wb;  // byte offsets of the step-index / wind A / wind B sections inside a block
+    int off_epi;              // byte offset of the episode row (the last 128 bytes of a block) = bytes the step kernel's bulk copy fetches
     const double *basis;      // [npieces][4][fp] cardinal not-a-knot spline basis
     const int *piece_bounds;  // [npieces][2] first / last wind sample index that piece_of() assigns to each spline piece
     float per_piece, inv_per_piece;  // Lm1 / npieces: wind samples per spline piece, and its reciprocal
@@ -205,6 +208,14 @@ __host__ __device__ __forceinline__ long long num_blocks(long long n_envs) { ret
 // Section `off` of the block that holds env i (global memory).
 __device__ __forceinline__ char *block_section(const DevCfg &c, long long i, int off) {
     return c.state + (i >> 5) * (long long)c.block_bytes + off;
+}
+
+// Step index (Boat.index) and episode number of env i (global memory).
+__device__ __forceinline__ uint32_t *index_ptr(const DevCfg &c, long long i) {
+    return reinterpret_cast<uint32_t *>(block_section(c, i, c.off_idx)) + (i & 31);
+}
+__device__ __forceinline__ uint32_t *episode_ptr(const DevCfg &c, long long i) {
+    return reinterpret_cast<uint32_t *>(block_section(c, i, c.off_epi)) + (i & 31);
 }
 
 // NS scalars of lane `lane` from a section (vector row v at sec + (v*32 + lane)*16).
