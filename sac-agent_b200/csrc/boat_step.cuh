@@ -502,13 +502,16 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             tma_load_1d(prev_base + buf * kTileBytes, prev_obs + (size_t)b * (32 * kObsDim), (uint32_t)kTileBytes, pfull + buf);
         }
     };
+    // K = 1 (HBM bound): the bulk copy stops before the episode row, which only an ending episode touches.
+    // K > 1 (issue bound): the whole block, the slow path then finds the episode number in shared memory.
+    const uint32_t tma_bytes = KMULTI ? (uint32_t)bb : (uint32_t)c.off_epi;
     if (lane == 0) {  // prologue: fill the pipeline
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
             const int q = seq + s * wstride;
             if (q < blk_end) {
-                mbar_expect_tx(full + s, (uint32_t)c.off_epi);   // everything but the episode row
-                tma_load_1d(stage_base + s * bb, c.state + (size_t)block_of(q) * (size_t)bb, (uint32_t)c.off_epi, full + s);
+                mbar_expect_tx(full + s, tma_bytes);
+                tma_load_1d(stage_base + s * bb, c.state + (size_t)block_of(q) * (size_t)bb, tma_bytes, full + s);
             }
         }
         if (fused_store) prev_prefetch(seq, 0);
@@ -539,8 +542,10 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
         load_vecs<T, D_COUNT>(reinterpret_cast<const char *>(sb), lane, d);
         if (kCurves) load_vecs<T, 4>(reinterpret_cast<const char *>(sb) + c.off_wa, lane, wa);
         if (WK == WIND_BOTH) load_vecs<T, 4>(reinterpret_cast<const char *>(sb) + c.off_wb, lane, wb);
+        const uint32_t epi_s = KMULTI ? reinterpret_cast<const uint32_t *>(sb + c.off_epi)[lane] : 0u;
         const uint32_t ixw = reinterpret_cast<const uint32_t *>(sb + c.off_idx)[lane];  // last LDS of the stage
         int index = (int)ixw;
+        uint32_t episode_k = epi_s;   // K > 1 only: this launch's view of the env's episode number
         __syncwarp();
         if (lane == 0) {
             // The stage is consumed: refill it kStages blocks ahead.  The block number carries a data
@@ -548,8 +553,8 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             // set), so the bulk copy cannot be issued before the warp's loads have returned.
             const int q = seq + kStages * wstride + (int)(ixw >> 31);
             if (q < blk_end) {
-                mbar_expect_tx(full + stage, (uint32_t)c.off_epi);
-                tma_load_1d(stage_base + stage * bb, c.state + (size_t)block_of(q) * (size_t)bb, (uint32_t)c.off_epi, full + stage);
+                mbar_expect_tx(full + stage, tma_bytes);
+                tma_load_1d(stage_base + stage * bb, c.state + (size_t)block_of(q) * (size_t)bb, tma_bytes, full + stage);
             }
         }
         if (++stage == kStages) { stage = 0; parity ^= 1u; }
@@ -697,7 +702,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                 // the episode number lives outside the streamed part of the block: fetched only here, written only
                 // when an episode ends
                 uint32_t *epi_g = reinterpret_cast<uint32_t *>(gb + c.off_epi) + lane;
-                uint32_t episode = (need_setup && active) ? *epi_g : 0u;
+                uint32_t episode = KMULTI ? episode_k : ((need_setup && active) ? *epi_g : 0u);
                 if (is_done) {  // statistics (info dict, boat_env.py:24-32,87-113): sparse events -> per-env REDs
                     double *cnt = c.counters + (blk & (kCounterSlots - 1)) * 32;
                     const double ret = (double)d[D_RET];
@@ -747,6 +752,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                     index = 0;
                     episode += 1u;
                     *epi_g = episode;
+                    episode_k = episode;
                     wind_dirty = false;  // the old episode's coefficients are dead; the follow-up kernel writes the new ones
                     stage_reset_obs<T>(c, row, (T)0);  // only experiment 2 starts off the centre line (:166-167)
                     deferred = true;
@@ -780,6 +786,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                             d[D_SY] = sy0;
                             index = 0;
                             episode = e_epi;
+                            episode_k = e_epi;
                             *epi_g = e_epi;
                             stage_reset_obs<T>(c, row, sy0);
                             if (!KMULTI) {
