@@ -198,6 +198,10 @@ __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], in
     d[D_SX] = s_x; d[D_SY] = s_y; d[D_SR] = s_r; d[D_RET] += r;
 }
 
+// A NaN bit pattern that no arithmetic instruction produces (their NaNs are canonical): see the stage-refill vote.
+__device__ __forceinline__ bool is_poison(float v) { return __float_as_uint(v) == 0x7fc00001u; }
+__device__ __forceinline__ bool is_poison(double v) { return __double_as_longlong(v) == 0x7ff8000000000001ll; }
+
 // return_state  boat_env.py:308-326: the 11 normalised observations of an env, written to
 // its row of the warp's shared-memory staging tile.  `index` = Boat.index after the step.
 __device__ __forceinline__ void stage_obs(const DevCfg &c, double *row, const double (&d)[D_COUNT],
@@ -543,15 +547,29 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
         if (kCurves) load_vecs<T, 4>(reinterpret_cast<const char *>(sb) + c.off_wa, lane, wa);
         if (WK == WIND_BOTH) load_vecs<T, 4>(reinterpret_cast<const char *>(sb) + c.off_wb, lane, wb);
         const uint32_t epi_s = KMULTI ? reinterpret_cast<const uint32_t *>(sb + c.off_epi)[lane] : 0u;
-        const uint32_t ixw = reinterpret_cast<const uint32_t *>(sb + c.off_idx)[lane];  // last LDS of the stage
+        const uint32_t ixw = reinterpret_cast<const uint32_t *>(sb + c.off_idx)[lane];
         int index = (int)ixw;
         uint32_t episode_k = epi_s;   // K > 1 only: this launch's view of the env's episode number
-        __syncwarp();
+        // The refill below overwrites this stage, so it must not be issued before EVERY lane's loads of the stage
+        // have returned (issuing them is not enough: a refill served from L2 can land within a few hundred
+        // cycles).  The vote consumes a register of each of the loads above in every lane -- the compiler is free
+        // to order them, so all of them take part -- and lane 0's block number depends on the vote: a true
+        // dependency for the hardware scoreboard.  The predicate is never true: a step index never reaches the
+        // poison value (indices stay below 2^20), no arithmetic produces the poison NaN, and the 0xFF fill of the
+        // padding lanes of a ragged last block is not the poison pattern either.
+        bool never = ixw == 0x7fc00001u || (KMULTI && epi_s == 0x7fc00001u && ixw == 0x7fc00002u);
+        constexpr int W = VecOf<T>::W;   // one register of every 16-byte vector load
+#pragma unroll
+        for (int v = 0; v < D_COUNT / W; ++v) never |= is_poison(d[v * W]);
+#pragma unroll
+        for (int v = 0; v < 4 / W; ++v) {
+            if (kCurves) never |= is_poison(wa[v * W]);
+            if (WK == WIND_BOTH) never |= is_poison(wb[v * W]);
+        }
+        const unsigned never_mask = __ballot_sync(FULL, never);
         if (lane == 0) {
-            // The stage is consumed: refill it kStages blocks ahead.  The block number carries a data
-            // dependency on the LAST shared-memory load of the stage (bit 31 of the step index is never
-            // set), so the bulk copy cannot be issued before the warp's loads have returned.
-            const int q = seq + kStages * wstride + (int)(ixw >> 31);
+            // The stage is consumed: refill it kStages blocks ahead.
+            const int q = seq + kStages * wstride + (never_mask != 0u ? 1 : 0);
             if (q < blk_end) {
                 mbar_expect_tx(full + stage, tma_bytes);
                 tma_load_1d(stage_base + stage * bb, c.state + (size_t)block_of(q) * (size_t)bb, tma_bytes, full + stage);

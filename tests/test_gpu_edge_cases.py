@@ -261,3 +261,25 @@ def test_env_state_host_and_zero_copy_errors(S):
     assert rc == 0 and np.array_equal(oh, o.cpu().numpy()) and np.array_equal(rh, r.cpu().numpy())
     assert np.array_equal(dh, d.cpu().numpy())
     env.close(); twin.close()
+
+
+def test_whole_launch_step_is_deterministic(S):
+    """Two identical handles stepped alternately with the same actions agree bit for bit: several state blocks per
+    persistent warp (the TMA stage is refilled while the warp computes), frequent resets, a ragged last block.
+    Regression test for the stage-refill race: a bulk copy served from L2 could land before the last
+    shared-memory loads of the stage had returned (profiles/determinism_check.py: 16 of 40 trials failed)."""
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    n = 300_003
+    for trial in range(6):
+        a = S.BatchedBoatEnv(cfg, n, seed=2, precision="fp32", device=0, auto_reset=True)
+        b = S.BatchedBoatEnv(cfg, n, seed=2, precision="fp32", device=0, auto_reset=True)
+        a.reset(); b.reset()
+        for t in range(14):
+            acts = a.uniform_actions(t, 4.0)
+            oa, ra, da, _ = a.step(acts)
+            torch.cuda.synchronize()
+            ob, rb, db, _ = b.step(acts)
+            torch.cuda.synchronize()
+            assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), (trial, t)
+        a.close(); b.close()
