@@ -2,7 +2,11 @@
 // registers across K fused sub-steps, in-kernel termination cascade, statistics and auto-reset.
 //   * persistent, self-contained step warps walk the 32-env state blocks of the tile-blocked layout
 //     (common.cuh); each keeps one TMA bulk copy (cp.async.bulk + mbarrier) of its next block in flight;
+//     (the copy skips the block's episode row, which only an ending episode touches, and is held back by a
+//     warp vote until every lane's loads of the stage being refilled have returned);
 //   * state goes back with 128-bit stores, the [32][11] observation tile with one bulk store;
+//   * the fused agent.remember variant also moves the previous observation tile to the replay ring through
+//     shared memory with bulk copies only;
 //   * K = 1 kernels of the random-wind experiments are warp-specialised: wind-setup requests travel
 //     through a shared-memory ring to dedicated setup warps (wind_setup.cuh does the maths).
 // Instantiated for float (production) in step_f32.cu and for double (validation, reference operation
