@@ -1,7 +1,8 @@
+"""Check and time boatagent_policy_act (csrc/policy_mlp.cu): against the fp32 policy and against the same arithmetic
+spelled out in PyTorch (bf16 operands, fp32 accumulation, fp32 heads), then 1,048,576 envs timed."""
 import sys, time
 sys.path.insert(0,'/root/repo')
 import torch, numpy as np
-import sac_agent_b200 as S
 from sac_agent_b200.networks import ActorNetwork, TensorCorePolicy
 torch.manual_seed(0)
 actor = ActorNetwork(None, (11,), np.array([1.0],dtype=np.float32), n_actions=1).cuda()

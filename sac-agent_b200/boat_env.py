@@ -10,7 +10,6 @@
 from __future__ import annotations
 
 import ctypes as C
-import types
 
 import numpy as np
 
