@@ -177,9 +177,14 @@ def cpu_baseline_leg(target_seconds: float = 12.0) -> dict:
         s_, d_ = port.sample(n_envs, t_steps)
         steps += s_
         dt += d_
+    # the same port on ONE core (BASELINE.md section 3 reports both): a ~2 s sample
+    one = CpuPort(1)
+    n1 = max(16, int(rate / cores * 2.0 / t_steps))
+    s1, d1 = one.sample(n1, t_steps)
     return {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{reps} x {n_envs} envs x {t_steps} steps, experiment {EXPERIMENT}, uniform(-1,1) actions, "
-                      f"auto-reset, oracle/boat_oracle.c with {cores} pthreads ({dt:.1f} s)"}
+                      f"auto-reset, oracle/boat_oracle.c with {cores} pthreads ({dt:.1f} s)",
+            "value_1core": s1 / d1, "sample_1core": f"{n1} envs x {t_steps} steps on one thread ({d1:.1f} s)"}
 
 
 def run_reference(args) -> None:
