@@ -96,6 +96,8 @@ def main(argv=None):
             for _ in range(args.updates_per_iter):
                 out = agent.learn()
                 losses = out if out is not None else losses
+        if pipe and args.log_every and it % args.log_every == 0:
+            pipe.sync()   # counters, losses and checkpoints below run on the default stream: order it after the pipeline
         if exp and args.log_every and it % args.log_every == 0:
             # one console.csv row per logging interval: the mean return of the episodes that ended in it
             c = env.counters()

@@ -123,7 +123,7 @@ BOATENV_API int boatenv_step_k(boatenv_t h, const void *actions, int64_t action_
 
 /* The same step through HOST buffers (pinned or pageable): copies actions H2D, steps,
  * copies obs/reward/done D2H, chunked over internal streams so that the copies overlap
- * the kernel.  Waits for all work queued on the device before it starts and blocks until
+ * the kernel.  Starts after the work queued on the legacy default stream and blocks until
  * the results are in host memory.  This is the end-to-end
  * call a CPU-side agent loop (main.py:80-81) makes.  Up to 2048 envs (the reference's single-env
  * loop included) it runs zero-copy instead: the kernel reads and writes mapped pinned memory
@@ -134,6 +134,19 @@ BOATENV_API int boatenv_step_host(boatenv_t h, const void *actions_host, void *o
  * single-env drop-in needs to maintain info['termination'] and its counters (boat_env.py:87-105). */
 BOATENV_API int boatenv_step_host_term(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host,
                            uint8_t *done_host, uint8_t *term_host, uint32_t flags);
+/* boatenv_step_host / _term order themselves after the work queued on the legacy default stream.  This variant
+ * names the caller's stream instead (the one its reset / step / learner kernels for this handle were queued on):
+ * the internal copy / compute streams wait for an EVENT recorded there -- never a device-wide synchronise, so a
+ * learner running on another stream of the same process keeps running.  term_host may be NULL.
+ * main.py:80-81 with a CPU-side agent. */
+BOATENV_API int boatenv_step_host_stream(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host,
+                             uint8_t *done_host, uint8_t *term_host, uint32_t flags, void *stream);
+/* K fused sub-steps (boatenv_step_k) through HOST buffers: actions_host T[K][n_envs] in, ONE observation /
+ * summed reward / done / termination code / executed-sub-step count per env out -- a host-side agent that
+ * repeats or plans K actions moves K times fewer bytes per env-step over PCIe.  term_host and steps_host
+ * (int32[n_envs]) may be NULL.  boat_env.py:67-115 K times per call. */
+BOATENV_API int boatenv_step_k_host(boatenv_t h, const void *actions_host, int32_t k, void *obs_host, void *reward_host,
+                        uint8_t *done_host, uint8_t *term_host, int32_t *steps_host, uint32_t flags, void *stream);
 
 /* ---- state access (env.boat.* of main.py:94, recorder.py:36,46) -------------------- */
 
@@ -171,6 +184,13 @@ BOATENV_API int boatenv_set_episode_draws(boatenv_t h, const int32_t *s_y_start,
  * (wind.py:78).  Lets a CPU reference be fed the identical episode randomness. */
 BOATENV_API int boatenv_episode_draws_host(const boatenv_params *params, uint64_t seed, int64_t global_env_id,
                                uint32_t episode, int32_t *s_y_start_out, double *knots_out);
+
+/* The same for n_ids global env ids and episodes [episode_begin, episode_begin + n_episodes) in one call
+ * (the sampled-subset parity tests at benchmark size draw 10^5 episodes):
+ *   s_y_start_out int32[n_episodes][n_ids] or NULL; knots_out double[n_episodes][n_ids][2][fixed_points] or NULL. */
+BOATENV_API int boatenv_episode_draws_batch_host(const boatenv_params *params, uint64_t seed,
+                               const int64_t *global_env_ids, int64_t n_ids, uint32_t episode_begin,
+                               int32_t n_episodes, int32_t *s_y_start_out, double *knots_out);
 
 /* ---- checkpoint / resume ----------------------------------------------------------- */
 
@@ -219,6 +239,9 @@ BOATENV_API int boatreplay_sample(boatreplay_t r, int64_t batch, uint64_t seed, 
 /* The gather of buffer.py:29-33 with caller-supplied indices int64[batch] (device). */
 BOATENV_API int boatreplay_gather(boatreplay_t r, int64_t batch, const int64_t *idx, void *s_out, void *a_out,
                       void *r_out, void *s2_out, uint8_t *done_out, void *stream);
+/* Checkpoint restore: sets the store counter (buffer.py:6 mem_cntr).  The next store goes to slot mem_cntr % mem_size,
+ * samples draw from [0, min(mem_cntr, mem_size)). */
+BOATENV_API int boatreplay_set_mem_cntr(boatreplay_t r, int64_t mem_cntr);
 BOATENV_API int64_t boatreplay_mem_cntr(boatreplay_t r); /* buffer.py:6  */
 BOATENV_API int64_t boatreplay_mem_size(boatreplay_t r); /* buffer.py:5  */
 
@@ -296,6 +319,11 @@ BOATENV_API int boattoy_reset(boattoy_t t, void *stream);
  * out: T[n_envs][4]: car {s_x, s_y, v, angle}; parachute {s, v, a, integrator calls}.
  * done_out uint8[n_envs] or NULL (parachute: s < 0 reached; the env then stays put). */
 BOATENV_API int boattoy_step(boattoy_t t, int32_t k, void *out, uint8_t *done_out, void *stream);
+/* HOST function (no GPU work): the per-env parameters that envs [env_begin, env_begin + n_envs) of a toy handle
+ * created with (params_host, jitter, seed) use -- out double[n_envs][n_params], env 0 = the script constants
+ * (toy_car.py:7-8,11,23; toy_parachute.py:8-15).  Lets a CPU reference run the jittered envs. */
+BOATENV_API int boattoy_params_host(int kind, const double *params_host, int32_t n_params, double jitter, uint64_t seed,
+                        int64_t env_begin, int64_t n_envs, double *out);
 
 /* ---- misc -------------------------------------------------------------------------- */
 BOATENV_API const char *boatenv_version(void);

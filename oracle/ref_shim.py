@@ -24,7 +24,20 @@ import types
 import numpy as np
 import yaml
 
-REFERENCE_ROOT = os.environ.get("SAC_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ROOT = os.path.join(_HERE, "_ref")   # oracle/make_ref.py: byte-for-byte copies, git-ignored, travel to the GPU box
+
+
+def _pick_root() -> str:
+    env = os.environ.get("SAC_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile(os.path.join("/root/reference", "environment", "boat_env.py")):
+        return "/root/reference"
+    return STAGED_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
@@ -68,6 +81,10 @@ def _install_stubs() -> None:
         gym.spaces = spaces
         sys.modules["gym"] = gym
         sys.modules["gym.spaces"] = spaces
+    if "dotmap" not in sys.modules:  # utils/config_reader.py:3
+        dm = types.ModuleType("dotmap")
+        dm.DotMap = AttrDict
+        sys.modules["dotmap"] = dm
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm", "seaborn"):
         if name not in sys.modules:
             sys.modules[name] = types.ModuleType(name)
@@ -113,11 +130,19 @@ def fixture_dir(n: int) -> str:
                         f"experiment_setting_{n}")
 
 
+def plot_free_experiment_dir() -> str:
+    """A directory that already holds a file named reward_field.png (reward_functions.py:23-26)."""
+    d = fixture_dir(1)
+    if os.path.isfile(os.path.join(d, "reward_field.png")):
+        return d
+    return os.path.join(STAGED_ROOT, "_experiment_dir")
+
+
 def make_env(cfg: AttrDict):
     """BoatEnv with an experiment_dir that already holds reward_field.png so the
     per-step os.path.exists (reward_functions.py:26) short-circuits the plot."""
     ref = import_reference()
-    exp = types.SimpleNamespace(experiment_dir=fixture_dir(1))
+    exp = types.SimpleNamespace(experiment_dir=plot_free_experiment_dir())
     return ref.BoatEnv(cfg, exp)
 
 
@@ -149,3 +174,33 @@ class KnotInjector:
     def __exit__(self, *exc):
         np.random.randint, np.random.sample = self._randint, self._sample
         return False
+
+
+def import_reference_agent(replay_buffer_cls=None):
+    """The reference's ``ContinuousAgent`` class (agent/continuous_agent.py:9).  With ``replay_buffer_cls`` the
+    module is imported with ``agent.buffer.ReplayBuffer`` replaced -- the import swap of INTEGRATION.md section 1
+    (agent/continuous_agent.py:4 ``from agent.buffer import ReplayBuffer``) without touching the file."""
+    import importlib
+    import_reference()
+    saved_buf = sys.modules.get("agent.buffer")
+    saved_agent = sys.modules.pop("agent.continuous_agent", None)
+    try:
+        if replay_buffer_cls is not None:
+            m = types.ModuleType("agent.buffer")
+            m.ReplayBuffer = replay_buffer_cls
+            sys.modules["agent.buffer"] = m
+        mod = importlib.import_module("agent.continuous_agent")
+        return mod.ContinuousAgent
+    finally:
+        sys.modules.pop("agent.continuous_agent", None)
+        if saved_agent is not None:
+            sys.modules["agent.continuous_agent"] = saved_agent
+        if saved_buf is not None:
+            sys.modules["agent.buffer"] = saved_buf
+
+
+def import_reference_recorder():
+    """postprocessing/recorder.py:7 ``Recorder``."""
+    import_reference()
+    from postprocessing.recorder import Recorder  # noqa
+    return Recorder

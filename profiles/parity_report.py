@@ -54,7 +54,65 @@ def case(experiment, precision, n, T, scale, auto_reset, episodes):
     env.close()
 
 
+def big_case(seed, precision, n, T, chunk=4096, scale=1.0, experiment=6, episodes=48):
+    """fp32 / fp64 auto-reset regime at scale: n envs in chunks (shards of one population: env_id_offset), T steps,
+    everything recorded on the device and compared once per chunk.  Counts EPISODES whose end differs."""
+    cfg = S.load_config(base_settings__experiment=experiment)
+    p = O.params_from_config(cfg)
+    tot_eps = mism_eps = 0
+    worst_obs = worst_rew = 0.0
+    kinds = {}
+    for off in range(0, n, chunk):
+        m = min(chunk, n - off)
+        env = S.BatchedBoatEnv(cfg, m, seed=seed, precision=precision, device=0, auto_reset=True, env_id_offset=off)
+        s_y, knots = env.episode_draws_batch(np.arange(m), episodes)
+        env.reset()
+        acts = torch.stack([env.uniform_actions(t, scale).clone() for t in range(T)])
+        obs = torch.empty((T, m, 11), dtype=env.dtype, device=env.device)
+        rew = torch.empty((T, m), dtype=env.dtype, device=env.device)
+        term = torch.empty((T, m), dtype=torch.uint8, device=env.device)
+        for t in range(T):
+            o, r, d, info = env.step(acts[t])
+            obs[t], rew[t], term[t] = o, r, info["term"]
+            obs[t] = torch.where((d > 0)[:, None], info["final_obs"], o)
+        ref = O.rollout(p, acts.double().cpu().numpy(), s_y, knots, auto_reset=True)
+        tm = term.cpu().numpy()
+        bad = tm != ref["term"]
+        # an env is comparable up to its first mismatch (afterwards the two are in different episodes)
+        first_bad = np.where(bad.any(axis=0), bad.argmax(axis=0), T)
+        live = np.arange(T)[:, None] < first_bad[None, :]
+        tot_eps += int((ref["term"] > 0).sum())
+        mism_eps += int(bad.any(axis=0).sum())
+        for i in np.nonzero(bad.any(axis=0))[0]:
+            t0 = int(first_bad[i])
+            k = f"ref={int(ref['term'][t0, i])},ours={int(tm[t0, i])}"
+            kinds[k] = kinds.get(k, 0) + 1
+        o = obs.double().cpu().numpy()
+        e_obs = np.abs(o - ref["obs"]) / np.maximum(np.abs(ref["obs"]), 1.0)
+        e_rew = np.abs(rew.double().cpu().numpy() - ref["reward"]) / np.maximum(np.abs(ref["reward"]), 1.0)
+        worst_obs = max(worst_obs, float(e_obs[live].max()))
+        worst_rew = max(worst_rew, float(e_rew[live].max()))
+        env.close()
+    print(json.dumps({"case": "big_auto_reset", "experiment": experiment, "precision": precision, "seed": seed,
+                      "n_envs": n, "steps": T, "action_scale": scale, "episodes_finished": tot_eps,
+                      "envs_with_a_termination_mismatch": mism_eps, "mismatch_kinds": kinds,
+                      "max_scaled_obs_err_before_first_mismatch": worst_obs,
+                      "max_scaled_reward_err_before_first_mismatch": worst_rew,
+                      "tolerance": 1e-9 if precision == "fp64" else 1e-4}), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "big":   # python profiles/parity_report.py big [n_envs] [steps] [seeds...]
+        n = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
+        T = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
+        seeds = [int(x) for x in sys.argv[4:]] or [1, 2, 3, 4, 5]
+        for seed in seeds:
+            big_case(seed, "fp32", n, T)
+        big_case(seeds[0], "fp64", min(n, 8192), T)
+        # goal / out-of-bounds regime: small steering noise, experiment 2 (random start), long episodes
+        for seed in seeds[:2]:
+            big_case(seed, "fp32", min(n, 8192), 6000, scale=0.03, experiment=2, episodes=8)
+        sys.exit(0)
     for exp in range(1, 7):
         for precision in ("fp64", "fp32"):
             case(exp, precision, 4096, 1000, 0.05, False, 1)

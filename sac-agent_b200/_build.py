@@ -49,12 +49,12 @@ def _deps_mtime() -> float:
     return m
 
 
-def _compile(unit: str, flags, verbose: bool) -> str:
+def _compile(unit: str, flags, verbose: bool, obj_dir: str = OBJ, variant_flags=()) -> str:
     src = os.path.join(CSRC, unit)
-    obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
+    obj = os.path.join(obj_dir, unit.replace(".cu", ".o"))
     if os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), _deps_mtime()):
         return obj
-    extra = os.environ.get("BOATENV_NVCC_FLAGS", "").split()  # tuning experiments only
+    extra = os.environ.get("BOATENV_NVCC_FLAGS", "").split() + list(variant_flags)  # tuning experiments only
     cmd = [nvcc(), *ARCH, *COMMON, *flags, *extra, "-c", src, "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
@@ -66,21 +66,29 @@ def _compile(unit: str, flags, verbose: bool) -> str:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OBJ, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, variant: str = "", variant_flags=()) -> str:
+    """Builds libboatenv.so.  ``variant`` (ablation experiments only, e.g. ("novote", ["-DBOAT_DEBUG_NO_REFILL_VOTE"]))
+    builds libboatenv_<variant>.so with the extra nvcc flags; select it at run time with BOATENV_LIBRARY=<path>."""
+    obj_dir = OBJ if not variant else os.path.join(CSRC, "_obj_" + variant)
+    lib = LIB if not variant else os.path.join(HERE, f"libboatenv_{variant}.so")
+    os.makedirs(obj_dir, exist_ok=True)
     if force:
-        for f in os.listdir(OBJ):
-            os.remove(os.path.join(OBJ, f))
+        for f in os.listdir(obj_dir):
+            os.remove(os.path.join(obj_dir, f))
     units = {u: fl for u, fl in UNITS.items() if os.path.exists(os.path.join(CSRC, u))}
     with cf.ThreadPoolExecutor(max_workers=len(units)) as ex:
-        objs = list(ex.map(lambda kv: _compile(kv[0], kv[1], verbose), units.items()))
-    if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [nvcc(), *ARCH, "-shared", "-o", LIB, *objs]
+        objs = list(ex.map(lambda kv: _compile(kv[0], kv[1], verbose, obj_dir, variant_flags), units.items()))
+    if (not os.path.exists(lib)) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in objs):
+        cmd = [nvcc(), *ARCH, "-shared", "-o", lib, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:  # python -m sac_agent_b200._build --variant novote -DBOAT_DEBUG_NO_REFILL_VOTE
+        i = sys.argv.index("--variant")
+        print(build(variant=sys.argv[i + 1], variant_flags=[a for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -23,7 +23,8 @@ class BoatEnvError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(HERE, _LIB_NAME)
+    """libboatenv.so next to this file; BOATENV_LIBRARY selects an ablation build (profiles/ experiments only)."""
+    return os.environ.get("BOATENV_LIBRARY") or os.path.join(HERE, _LIB_NAME)
 
 
 _lib = None
@@ -40,6 +41,8 @@ SIGNATURES = {
     "boatenv_step_k": (C.c_int, [vp, vp, i64, i32, vp, vp, vp, vp, vp, u32, vp]),
     "boatenv_step_host": (C.c_int, [vp, vp, vp, vp, vp, u32]),
     "boatenv_step_host_term": (C.c_int, [vp, vp, vp, vp, vp, vp, u32]),
+    "boatenv_step_host_stream": (C.c_int, [vp, vp, vp, vp, vp, vp, u32, vp]),
+    "boatenv_step_k_host": (C.c_int, [vp, vp, i32, vp, vp, vp, vp, vp, u32, vp]),
     "boatenv_get_field": (C.c_int, [vp, C.c_int, vp, vp]),
     "boatenv_set_field": (C.c_int, [vp, C.c_int, vp, vp]),
     "boatenv_env_state_host": (C.c_int, [vp, i64, C.POINTER(dbl)]),
@@ -47,6 +50,7 @@ SIGNATURES = {
     "boatenv_wind_length": (C.c_int, [vp]),
     "boatenv_set_episode_draws": (C.c_int, [vp, vp, vp, vp]),
     "boatenv_episode_draws_host": (C.c_int, [PP, u64, i64, u32, C.POINTER(i32), C.POINTER(dbl)]),
+    "boatenv_episode_draws_batch_host": (C.c_int, [PP, u64, vp, i64, u32, i32, vp, vp]),
     "boatenv_state_bytes": (i64, [vp]),
     "boatenv_export_state": (C.c_int, [vp, vp, vp]),
     "boatenv_import_state": (C.c_int, [vp, vp, vp]),
@@ -63,12 +67,14 @@ SIGNATURES = {
     "boatreplay_sample": (C.c_int, [vp, i64, u64, u64, vp, vp, vp, vp, vp, vp, vp]),
     "boatreplay_gather": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),
     "boatreplay_mem_cntr": (i64, [vp]),
+    "boatreplay_set_mem_cntr": (C.c_int, [vp, i64]),
     "boatreplay_mem_size": (i64, [vp]),
     "boatenv_step_store": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, u32, vp]),
     "boattoy_create": (C.c_int, [C.c_int, i64, C.POINTER(dbl), i32, dbl, u64, C.c_int, C.c_int, C.POINTER(vp)]),
     "boattoy_destroy": (C.c_int, [vp]),
     "boattoy_reset": (C.c_int, [vp, vp]),
     "boattoy_step": (C.c_int, [vp, i32, vp, vp, vp]),
+    "boattoy_params_host": (C.c_int, [C.c_int, C.POINTER(dbl), i32, dbl, u64, i64, i64, vp]),
     "boatenv_version": (C.c_char_p, []),
     "boatenv_error_string": (C.c_char_p, [C.c_int]),
     "boatenv_kernel_launches": (i64, []),

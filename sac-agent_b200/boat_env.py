@@ -141,13 +141,28 @@ class BatchedBoatEnv:
                                           steps_out.data_ptr(), flags, self._stream()), "boatenv_step_k")
         return self.obs, self.reward, self.done, {"term": self.term, "steps": steps_out}
 
-    def step_host(self, actions_host, obs_host, reward_host, done_host):
+    def step_host(self, actions_host, obs_host, reward_host, done_host, term_host=None):
         """End-to-end step through HOST (ideally pinned) buffers; blocks until the results
-        are in host memory."""
+        are in host memory.  Ordered after the work queued on torch's current stream (an event wait,
+        no device-wide synchronise)."""
         flags = AUTO_RESET if self.auto_reset else 0
-        _lib.check(self._L.boatenv_step_host(self._h, actions_host.data_ptr(), obs_host.data_ptr(),
-                                             reward_host.data_ptr(), done_host.data_ptr(), flags),
-                   "boatenv_step_host")
+        _lib.check(self._L.boatenv_step_host_stream(self._h, actions_host.data_ptr(), obs_host.data_ptr(),
+                                                    reward_host.data_ptr(), done_host.data_ptr(),
+                                                    None if term_host is None else term_host.data_ptr(), flags,
+                                                    self._stream()), "boatenv_step_host_stream")
+        return obs_host, reward_host, done_host
+
+    def step_k_host(self, actions_host, k, obs_host, reward_host, done_host, term_host=None, steps_host=None):
+        """K fused sub-steps through HOST buffers: ``actions_host`` [k, n_envs] in, one observation / summed
+        reward / done (/ termination code / executed sub-steps) per env out."""
+        flags = AUTO_RESET if self.auto_reset else 0
+        if tuple(actions_host.shape) != (int(k), self.n_envs):
+            raise ValueError("actions_host must be [k, n_envs]")
+        _lib.check(self._L.boatenv_step_k_host(self._h, actions_host.data_ptr(), int(k), obs_host.data_ptr(),
+                                               reward_host.data_ptr(), done_host.data_ptr(),
+                                               None if term_host is None else term_host.data_ptr(),
+                                               None if steps_host is None else steps_host.data_ptr(), flags,
+                                               self._stream()), "boatenv_step_k_host")
         return obs_host, reward_host, done_host
 
     # -- state access ------------------------------------------------------------------
@@ -206,6 +221,18 @@ class BatchedBoatEnv:
                                                       self.env_id_offset + int(env_index), int(episode),
                                                       C.byref(s), k), "boatenv_episode_draws_host")
         return int(s.value), np.array(k[:], dtype=np.float64).reshape(2, fp)
+
+    def episode_draws_batch(self, env_indices, episodes, episode_begin=0):
+        """The Philox draws of many (env, episode) pairs in one host call:
+        (s_y_start int32[episodes, M], knots float64[episodes, M, 2, fixed_points])."""
+        fp = int(self.params.fixed_points)
+        ids = np.ascontiguousarray(np.asarray(env_indices, dtype=np.int64) + self.env_id_offset)
+        s_y = np.empty((int(episodes), len(ids)), dtype=np.int32)
+        knots = np.empty((int(episodes), len(ids), 2, fp), dtype=np.float64)
+        _lib.check(self._L.boatenv_episode_draws_batch_host(C.byref(self.params), self.seed, ids.ctypes.data, len(ids),
+                                                            int(episode_begin), int(episodes), s_y.ctypes.data,
+                                                            knots.ctypes.data), "boatenv_episode_draws_batch_host")
+        return s_y, knots
 
     # -- checkpoint / resume -----------------------------------------------------------
     def state_dict(self):

@@ -146,6 +146,36 @@ class ReplayBuffer:
                    "boatreplay_gather")
         return self._finish(s, a, r, s2, d, self.as_torch if as_torch is None else as_torch)
 
+    # -- checkpoint / resume -----------------------------------------
+    def state_dict(self):
+        """The ring's five arrays (only the rows written so far), its store counter and its Philox sample counter:
+        a restored buffer stores to the same slots and draws the same batches."""
+        torch = _torch()
+        n = min(self.mem_cntr, self.mem_size)
+        s, a, r, s2, d = self._outputs(n) if n else self._outputs(0)
+        if n:
+            idx = torch.arange(n, dtype=torch.int64, device=self.device)
+            _lib.check(self._L.boatreplay_gather(self._h, n, idx.data_ptr(), s.data_ptr(), a.data_ptr(), r.data_ptr(),
+                                                 s2.data_ptr(), d.data_ptr(), self._stream()), "boatreplay_gather")
+        return {"state": s, "action": a, "reward": r, "new_state": s2, "terminal": d, "mem_cntr": self.mem_cntr,
+                "mem_size": self.mem_size, "samples": self._samples, "seed": self.seed, "precision": self.precision}
+
+    def load_state_dict(self, sd):
+        torch = _torch()
+        if int(sd["mem_size"]) != self.mem_size or int(sd["precision"]) != self.precision:
+            raise ValueError("checkpoint was taken from a ring of another size / precision")
+        n = min(int(sd["mem_cntr"]), self.mem_size)
+        _lib.check(self._L.boatreplay_set_mem_cntr(self._h, 0), "boatreplay_set_mem_cntr")
+        if n:   # rows 0..n-1 go back to slots 0..n-1, then the counter jumps to its old value
+            mv = lambda t, dt: t.to(device=self.device, dtype=dt).contiguous()  # noqa: E731
+            _lib.check(self._L.boatreplay_store(self._h, n, mv(sd["state"], self.dtype).data_ptr(),
+                                                mv(sd["action"], self.dtype).data_ptr(), mv(sd["reward"], self.dtype).data_ptr(),
+                                                mv(sd["new_state"], self.dtype).data_ptr(),
+                                                mv(sd["terminal"], torch.uint8).data_ptr(), self._stream()), "boatreplay_store")
+            torch.cuda.current_stream(self.device).synchronize()   # the staging tensors above die here
+        _lib.check(self._L.boatreplay_set_mem_cntr(self._h, int(sd["mem_cntr"])), "boatreplay_set_mem_cntr")
+        self._samples, self.seed = int(sd["samples"]), int(sd["seed"])
+
     # -- fused env.step + agent.remember (main.py:81-88) ---------------------------------
     def step_store(self, env, actions, done_flag_mode=1):
         """Steps every env of ``env`` (a BatchedBoatEnv) and writes the transitions

@@ -10,19 +10,23 @@ import ctypes as C
 
 import yaml
 
-# The values the hot path reads, with the defaults the reference ships in configs/original_config.yaml
-# (:7-9 base settings, :25-27 track, :32-54 boat model, :63-65 wind), plus the `agent:` block
-# (:13-22) that the SAC example uses.  Keys the env never reads (n_games,
-# render_skip_size, boat.n_max/w/aspect_ratio/a/b, agent.layer*_size) are not carried.
+# Every key of the reference's configs/original_config.yaml with the value it ships (:2-65): the hot path reads
+# base_settings.test_mode/dt/t_max/experiment, boat_env.*, most of boat.* and wind.*; the SAC example reads the
+# `agent:` block; the rest (n_games, render_skip_size, avg_lookback, boat.n_max/w/aspect_ratio/a/b,
+# agent.layer*_size) is carried because the reference's post-processing reads a run's configs/tuned_configs.yaml
+# (rendering/boat_env_render.py:31, postprocessing/replayer.py:52 use base_settings.avg_lookback).
 DEFAULTS = {
-    "base_settings": {"test_mode": 0, "dt": 0.25, "t_max": 2500, "experiment": 5},
-    "boat_env": {"track_width": 800, "boat_out_of_bounds_offset": 0, "goal_line": 3900},
-    "boat": {"fuel": 15000, "boat_m": 600, "boat_m_x": 50, "boat_m_y": 100, "boat_I": 6_000_000, "boat_Iz": 10,
-             "propeller_diameter": 1, "wake_friction": 0.3, "c_r_front": 0.31, "c_r_side": 2, "thrust_deduction": 0.3,
-             "rho": 1, "boat_area_front": 20, "boat_area_side": 90, "boat_l": 15, "boat_b": 6, "rudder_area": 10},
-    "wind": {"fixed_points": 8, "max_velocity": 0.5, "direction": 90},
+    "base_settings": {"test_mode": 0, "n_games": 250, "render_skip_size": 50, "avg_lookback": 50, "dt": 0.25,
+                      "t_max": 2500, "experiment": 5},
     "agent": {"learning_rate_alpha": 0.005, "learning_rate_beta": 0.0003, "gamma": 0.99,
-              "tvn_parameter_modulation_tau": 0.005, "max_size": 1_000_000, "batch_size": 1024, "reward_scale": 10},
+              "tvn_parameter_modulation_tau": 0.005, "max_size": 1_000_000, "layer1_size": 256, "layer2_size": 256,
+              "batch_size": 1024, "reward_scale": 10},
+    "boat_env": {"track_width": 800, "boat_out_of_bounds_offset": 0, "goal_line": 3900},
+    "boat": {"n_max": 30, "fuel": 15000, "w": 0.3, "boat_m": 600, "boat_m_x": 50, "boat_m_y": 100,
+             "boat_I": 6_000_000, "boat_Iz": 10, "propeller_diameter": 1, "wake_friction": 0.3, "c_r_front": 0.31,
+             "c_r_side": 2, "thrust_deduction": 0.3, "rho": 1, "boat_area_front": 20, "boat_area_side": 90,
+             "boat_l": 15, "boat_b": 6, "rudder_area": 10, "aspect_ratio": 2, "a": 4.252, "b": 0.262},
+    "wind": {"fixed_points": 8, "max_velocity": 0.5, "direction": 90},
 }
 
 

@@ -72,6 +72,8 @@ class DeviceAdam:
     def step(self, grads):
         """grads: one contiguous float32 tensor per parameter, in construction order."""
         for k, g in enumerate(grads):
+            if g.dtype != torch.float32 or not g.is_contiguous() or g.shape != self.params[k].shape:
+                raise ValueError(f"DeviceAdam.step: gradient {k} must be a contiguous float32 tensor of the parameter's shape")
             self._slots[k].grad = g.data_ptr()
         with torch.cuda.device(self.params[0].device):  # the ABI launches on the current device
             stream = torch.cuda.current_stream().cuda_stream
@@ -210,6 +212,7 @@ class ContinuousAgent:
         # whole forward pass and the draw in one launch, weights re-packed after every update)
         self.policy_precision = policy_precision
         self._tc_policy = None
+        self._weight_listeners = []   # callables run after load_models / load_state_dict (acting copies republish)
         B, O, A = self.batch_size, int(np.prod(self.input_dims)), self.get_n_actions()
         kw = dict(dtype=torch.float32, device=self.device)
         # static inputs of the captured update: sample_buffer writes them in place
@@ -353,12 +356,62 @@ class ContinuousAgent:
         self.learner.update_network_parameters(tau)
 
     def save_models(self):
+        """base_network.py:13-14 for the five networks (weights only, the reference's checkpoint format)."""
         for net in self.learner.networks():
             net.save_checkpoint()
 
     def load_models(self):
+        """base_network.py:16-17; the derived acting copies (the packed bf16 blob of the tcgen05 policy) follow."""
         for net in self.learner.networks():
             net.load_checkpoint()
+        self._weights_changed()
+
+    def _weights_changed(self):
+        if self._tc_policy is not None:
+            self._tc_policy.refresh()
+        for hook in self._weight_listeners:
+            hook()
+
+    # -- full training-state checkpoint (SURVEY.md 8f rank 4) -------------------------------------------------------
+    def state_dict(self):
+        """Everything `learn()` depends on beyond the env: the five networks, the Adam moments and step counter
+        (`DeviceAdam`), the replay ring with its store counter and its Philox sample counter, the update count.
+        The reference saves weights only (base_network.py:13-17) and loses the rest on restart."""
+        L = self.learner
+        return {"networks": {net.name: net.state_dict() for net in L.networks()},
+                "optimizer": {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone())
+                              for k, v in L.optimizer.state_dict().items()},
+                "memory": self.memory.state_dict(), "updates": self.updates,
+                "rng": torch.cuda.get_rng_state(self.device)}
+
+    def load_state_dict(self, sd):
+        L = self.learner
+        for net in L.networks():
+            net.load_state_dict(sd["networks"][net.name])
+        cur = L.optimizer.state_dict()
+        with torch.no_grad():
+            for k, v in sd["optimizer"].items():
+                if isinstance(v, list):
+                    torch._foreach_copy_(cur[k], [t.to(self.device) for t in v])
+                else:
+                    cur[k].copy_(v.to(self.device))
+        self.memory.load_state_dict(sd["memory"])
+        self.updates = int(sd["updates"])
+        torch.cuda.set_rng_state(sd["rng"].cpu(), self.device)
+        self._weights_changed()
+
+    def save_training_state(self, path=None):
+        """torch.save of `state_dict()` next to the reference-format checkpoints (<experiment_dir>/checkpoints/
+        training_state.pt)."""
+        import os
+        path = path or os.path.join(self.actor.checkpoints_dir, "training_state.pt")
+        torch.save(self.state_dict(), path)
+        return path
+
+    def load_training_state(self, path=None):
+        import os
+        path = path or os.path.join(self.actor.checkpoints_dir, "training_state.pt")
+        self.load_state_dict(torch.load(path, map_location=self.device, weights_only=False))
 
 
 class OverlappedActorLearner:
@@ -377,6 +430,10 @@ class OverlappedActorLearner:
     Events order everything that shares memory: the ring rows of step t are complete before sample(t);
     sample(t) has read the ring before step(t + 1) may overwrite its oldest rows; a copy is published
     only after the policy launch that read it has finished, and read only after it was published.
+
+    The two streams are NON-BLOCKING: nothing the caller does on its own (default) stream is ordered against them.
+    Call ``sync()`` before saving checkpoints, reading ``env.counters()`` or the losses, or loading weights; the
+    next ``step()`` then waits for the caller's stream in turn.  ``finish()`` is ``sync()`` at the end of a run.
     """
 
     def __init__(self, agent: ContinuousAgent, env, done_flag_mode=1):
@@ -394,6 +451,8 @@ class OverlappedActorLearner:
         self._policy = [None, None]   # (graph, static action tensor) per acting copy
         self.t = 0
         self.losses = None
+        self._rejoin = False
+        agent._weight_listeners.append(self._republish)
         cur = torch.cuda.current_stream(dev)
         self.s_env.wait_stream(cur)
         self.s_learn.wait_stream(cur)
@@ -427,6 +486,11 @@ class OverlappedActorLearner:
     def step(self):
         """One env step over all envs and (once the memory holds a batch) one update."""
         a, k = self.agent, self.t & 1
+        if self._rejoin:   # after sync(): whatever the caller did on its stream (checkpoint, counters) comes first
+            cur = torch.cuda.current_stream(a.device)
+            self.s_env.wait_stream(cur)
+            self.s_learn.wait_stream(cur)
+            self._rejoin = False
         with torch.cuda.stream(self.s_env):
             self.s_env.wait_event(self.ev_published[k])     # update(t - 2) has been written into acting[k]
             actions = self._act(k)
@@ -450,6 +514,24 @@ class OverlappedActorLearner:
 
     def finish(self):
         """Joins both streams into the caller's stream."""
+        self.sync()
+
+    def sync(self):
+        """Makes the caller's current stream wait for both pipeline streams, and the pipeline's next step wait for
+        the caller's stream.  REQUIRED before anything outside the pipeline touches what it owns -- agent.save_models()
+        / save_training_state(), env.counters(), reading the losses, agent.load_models(): the two streams are
+        non-blocking, the default stream is not ordered against them (torch.save would otherwise copy weights while
+        the fused Adam + Polyak kernel rewrites them)."""
         cur = torch.cuda.current_stream(self.agent.device)
         cur.wait_stream(self.s_env)
         cur.wait_stream(self.s_learn)
+        self._rejoin = True
+
+    def _republish(self):
+        """The actor was replaced from outside (load_models): both acting copies follow."""
+        with torch.no_grad():
+            for c in self.acting:
+                torch._foreach_copy_(list(c.parameters()), list(self.agent.actor.parameters()))
+        for p in self._policy:
+            if p is not None and hasattr(p, "refresh"):
+                p.refresh()

@@ -41,7 +41,10 @@ struct boatenv_handle {
     void *h_act, *h_obs, *h_rew;
     uint8_t *h_done, *h_term;
     cudaStream_t copy_in, compute, copy_out;
-    cudaEvent_t ev_in[8], ev_k[8];
+    cudaEvent_t ev_in[8], ev_k[8], ev_caller;
+    int32_t *h_steps;          // step_k_host: executed sub-steps per env
+    void *h_act_k;             // step_k_host: [K][n_envs] action staging (grown on demand)
+    int h_act_k_rows;
     bool host_path_ready;
     // small-N zero-copy staging: one mapped pinned allocation the kernels read / write over PCIe directly
     // (no copy engine, one launch + one synchronize per call): [act | obs | rew | done | term | 10 doubles]
@@ -133,7 +136,7 @@ static int derive_config(const boatenv_params *p, DevCfg &c) {
     }
     c.npieces = c.fp - 1;
     const double Ld = p->t_max / p->dt;  // wind.py:14-15
-    if (!(Ld >= 2.0) || Ld > 1048576.0) return BOATENV_EUNSUPPORTED;  // fp32 root location in wind_setup_warp
+    if (!(Ld >= 2.0) || Ld > 1048576.0 - 64.0) return BOATENV_EUNSUPPORTED;  // fp32 root location in wind_setup_warp; 20-bit step index
     if (Ld < 4.0) return BOATENV_EUNSUPPORTED;
     c.L = (int)Ld;
     c.Lm1 = c.L - 1;
@@ -219,6 +222,24 @@ static int derive_config(const boatenv_params *p, DevCfg &c) {
     f.rew_k = (float)(-0.03 / 3.4);
     f.rew_y0 = (float)(p->track_width * 0.2);
     f.inv_Lm1 = (float)c.inv_Lm1;
+    {   // fixed-point carriers of the fp32 mode (struct Fx<float>): the largest shifts that leave headroom
+        // beyond the termination thresholds (positions saturate instead of wrapping in the unstable regime)
+        auto shift_for = [](double reach) {
+            int sh = 30;
+            while (sh > 0 && reach * (double)(1LL << sh) >= 2147483647.0) --sh;
+            return sh;
+        };
+        f.sx_shift = shift_for(std::fabs(p->goal_line) * 1.02 + 16.0);
+        f.sy_shift = shift_for((std::fabs(p->track_width) + std::fabs(p->oob_offset)) * 1.02 + 16.0);
+        f.sx_k = (float)(p->dt * (double)(1LL << f.sx_shift));
+        f.sy_k = (float)(p->dt * (double)(1LL << f.sy_shift));
+        f.sx_inv = (float)(1.0 / (double)(1LL << f.sx_shift));
+        f.sy_inv = (float)(1.0 / (double)(1LL << f.sy_shift));
+        f.sx_goal = (int)std::ceil(p->goal_line * (double)(1LL << f.sx_shift));
+        f.sy_oob = (int)std::floor((p->track_width + p->oob_offset) * (double)(1LL << f.sy_shift));
+        f.rud_pi3 = (long long)std::floor((PI / 3.0) * 4398046511104.0);
+        f.rud_pi4 = (long long)std::floor((PI / 4.0) * 4398046511104.0);
+    }
     return BOATENV_OK;
 }
 
@@ -256,7 +277,8 @@ int boatenv_create(const boatenv_params *params, int64_t n_envs, uint64_t seed, 
     if (rc) return rc;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return BOATENV_ENODEVICE;
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard _guard(device);
+    if (!_guard.ok()) return (int)_guard.error();
     boatenv_handle *h = new (std::nothrow) boatenv_handle();
     if (!h) return BOATENV_EINVAL;
     std::memset(h, 0, sizeof(*h));
@@ -312,7 +334,7 @@ int boatenv_create(const boatenv_params *params, int64_t n_envs, uint64_t seed, 
 
 int boatenv_destroy(boatenv_t h) {
     if (!h) return BOATENV_EINVAL;
-    cudaSetDevice(h->device);
+    DeviceGuard _guard(h->device);
     cudaFree(h->cfg.state);
     cudaFree(h->cfg.counters);
     cudaFree(h->counters_out_dev);
@@ -327,12 +349,15 @@ int boatenv_destroy(boatenv_t h) {
     cudaFree(h->h_rew);
     cudaFree(h->h_done);
     cudaFree(h->h_term);
+    cudaFree(h->h_steps);
+    cudaFree(h->h_act_k);
     if (h->zc_host) cudaFreeHost(h->zc_host);
     if (h->host_path_ready) {
         cudaStreamDestroy(h->copy_in);
         cudaStreamDestroy(h->compute);
         cudaStreamDestroy(h->copy_out);
         for (int i = 0; i < 8; ++i) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
+        cudaEventDestroy(h->ev_caller);
     }
     delete h;
     return BOATENV_OK;
@@ -340,7 +365,7 @@ int boatenv_destroy(boatenv_t h) {
 
 int boatenv_reset(boatenv_t h, const uint8_t *mask, void *obs_out, void *stream) {
     if (!h) return BOATENV_EINVAL;
-    CUDA_TRY(cudaSetDevice(h->device));
+    GUARD_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(h->precision == 32 ? launch_reset_f32(h->cfg, mask, obs_out, st)
                                 : launch_reset_f64(h->cfg, mask, obs_out, st));
@@ -353,7 +378,7 @@ static int step_common(boatenv_t h, StepArgs &a, cudaStream_t st) {
     a.reverse = (int)(h->launch_parity++ & 1u);
     if (!a.actions || !a.obs_out || !a.reward_out || !a.done_out || a.ksteps < 1) return BOATENV_EINVAL;
     if (!aligned16(a.obs_out)) return BOATENV_EALIGN;
-    CUDA_TRY(cudaSetDevice(h->device));
+    GUARD_DEVICE(h);
     CUDA_TRY(h->precision == 32 ? launch_step_f32(h->cfg, a, st) : launch_step_f64(h->cfg, a, st));
     return BOATENV_OK;
 }
@@ -396,7 +421,7 @@ int boatenv_step_k(boatenv_t h, const void *actions, int64_t action_stride, int3
     a.flags = flags;
     if (k > 1 && h->cfg.ncurves > 0 && (flags & BOATENV_AUTO_RESET)) {  // episode-end queue of the fused kernels
         if (!h->kq_entries) {
-            CUDA_TRY(cudaSetDevice(h->device));
+            GUARD_DEVICE(h);
             h->kq_total = num_blocks(h->cfg.n_envs) * 32 + 1024LL * kWarpsPerCta * 32;
             CUDA_TRY(cudaMalloc((void **)&h->kq_entries, (size_t)h->kq_total * sizeof(uint2)));
             CUDA_TRY(cudaMalloc((void **)&h->kq_counts, 4096 * sizeof(unsigned)));
@@ -423,12 +448,13 @@ static int ensure_host_path(boatenv_t h) {
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
     }
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_caller, cudaEventDisableTiming));
     h->host_path_ready = true;
     return BOATENV_OK;
 }
 
-static int step_host_impl(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host, uint8_t *done_host,
-                          uint8_t *term_host, uint32_t flags);
+static int step_host_impl(boatenv_t h, const void *actions_host, int k, void *obs_host, void *reward_host,
+                          uint8_t *done_host, uint8_t *term_host, int32_t *steps_host, uint32_t flags, cudaStream_t caller);
 
 static int ensure_zero_copy(boatenv_t h) {
     if (h->zc_host) return BOATENV_OK;
@@ -483,52 +509,99 @@ static int step_host_zero_copy(boatenv_t h, const void *actions_host, void *obs_
 
 int boatenv_step_host(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host, uint8_t *done_host,
                       uint32_t flags) {
-    return step_host_impl(h, actions_host, obs_host, reward_host, done_host, nullptr, flags);
+    return step_host_impl(h, actions_host, 1, obs_host, reward_host, done_host, nullptr, nullptr, flags, nullptr);
 }
 
 int boatenv_step_host_term(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host,
                            uint8_t *done_host, uint8_t *term_host, uint32_t flags) {
     if (!term_host) return BOATENV_EINVAL;
-    return step_host_impl(h, actions_host, obs_host, reward_host, done_host, term_host, flags);
+    return step_host_impl(h, actions_host, 1, obs_host, reward_host, done_host, term_host, nullptr, flags, nullptr);
 }
 
-static int step_host_impl(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host, uint8_t *done_host,
-                          uint8_t *term_host, uint32_t flags) {
+int boatenv_step_host_stream(boatenv_t h, const void *actions_host, void *obs_host, void *reward_host,
+                             uint8_t *done_host, uint8_t *term_host, uint32_t flags, void *stream) {
+    return step_host_impl(h, actions_host, 1, obs_host, reward_host, done_host, term_host, nullptr, flags,
+                          (cudaStream_t)stream);
+}
+
+int boatenv_step_k_host(boatenv_t h, const void *actions_host, int32_t k, void *obs_host, void *reward_host,
+                        uint8_t *done_host, uint8_t *term_host, int32_t *steps_host, uint32_t flags, void *stream) {
+    if (k < 1) return BOATENV_EINVAL;
+    return step_host_impl(h, actions_host, k, obs_host, reward_host, done_host, term_host, steps_host, flags,
+                          (cudaStream_t)stream);
+}
+
+// Host-buffer step: H2D of the actions, the step kernel and the D2H of its outputs run as a chunked pipeline on
+// three streams of the handle.  `caller` is the stream the caller has been queueing work for this handle on
+// (reset / step / learner kernels): the pipeline waits for an event recorded there -- no device-wide synchronise,
+// so a learner running on another stream of the same process is not serialised against this call.
+static int step_host_impl(boatenv_t h, const void *actions_host, int k, void *obs_host, void *reward_host,
+                          uint8_t *done_host, uint8_t *term_host, int32_t *steps_host, uint32_t flags, cudaStream_t caller) {
     if (!h || !actions_host || !obs_host || !reward_host || !done_host) return BOATENV_EINVAL;
     if (!h->was_reset) return BOATENV_ESTATE;
-    CUDA_TRY(cudaSetDevice(h->device));
+    GUARD_DEVICE(h);
     int rc = ensure_host_path(h);
     if (rc) return rc;
-    // The copies and launches below run on the handle's own streams: order them after whatever the
-    // caller has queued on this device (a reset / step on its stream) -- this call is blocking anyway.
-    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaEventRecord(h->ev_caller, caller));
+    CUDA_TRY(cudaStreamWaitEvent(h->copy_in, h->ev_caller, 0));
+    CUDA_TRY(cudaStreamWaitEvent(h->compute, h->ev_caller, 0));
     const long long n = h->cfg.n_envs;
-    if (n <= kZeroCopyMaxEnvs) return step_host_zero_copy(h, actions_host, obs_host, reward_host, done_host, term_host, flags);
+    if (k == 1 && !steps_host && n <= kZeroCopyMaxEnvs)
+        return step_host_zero_copy(h, actions_host, obs_host, reward_host, done_host, term_host, flags);
+    const size_t es = h->esize;
+    void *act_dev = h->h_act;
+    if (k > 1) {  // [K][n] staging
+        if (h->h_act_k_rows < k) {
+            cudaFree(h->h_act_k);
+            h->h_act_k = nullptr;
+            h->h_act_k_rows = 0;
+            CUDA_TRY(cudaMalloc(&h->h_act_k, (size_t)k * (size_t)n * es));
+            h->h_act_k_rows = k;
+        }
+        act_dev = h->h_act_k;
+        if (steps_host && !h->h_steps) CUDA_TRY(cudaMalloc((void **)&h->h_steps, (size_t)n * sizeof(int32_t)));
+        if (h->cfg.ncurves > 0 && (flags & BOATENV_AUTO_RESET) && !h->kq_entries) {  // episode-end queue of the fused kernels
+            h->kq_total = num_blocks(n) * 32 + 1024LL * kWarpsPerCta * 32;
+            CUDA_TRY(cudaMalloc((void **)&h->kq_entries, (size_t)h->kq_total * sizeof(uint2)));
+            CUDA_TRY(cudaMalloc((void **)&h->kq_counts, 4096 * sizeof(unsigned)));
+        }
+    }
     // chunks are multiples of the CTA tile so that every tile keeps its 16-byte alignment
     int nchunks = n >= 8LL * 65536 ? 8 : (n >= 4LL * 65536 ? 4 : 1);
     long long per = ((n + nchunks - 1) / nchunks + kTile - 1) / kTile * kTile;
-    const size_t es = h->esize;
     const int rev = (int)(h->launch_parity++ & 1u);
     for (int cidx = 0; cidx < nchunks; ++cidx) {
         const long long b = (long long)cidx * per, e = std::min(n, b + per);
         if (b >= e) break;
         const size_t cnt = (size_t)(e - b);
-        CUDA_TRY(cudaMemcpyAsync((char *)h->h_act + b * es, (const char *)actions_host + b * es, cnt * es,
-                                 cudaMemcpyHostToDevice, h->copy_in));
+        if (k == 1) {
+            CUDA_TRY(cudaMemcpyAsync((char *)act_dev + b * es, (const char *)actions_host + b * es, cnt * es,
+                                     cudaMemcpyHostToDevice, h->copy_in));
+        } else {  // rows k of the [K][n] action matrix, columns [b, e)
+            CUDA_TRY(cudaMemcpy2DAsync((char *)act_dev + b * es, (size_t)n * es, (const char *)actions_host + b * es,
+                                       (size_t)n * es, cnt * es, (size_t)k, cudaMemcpyHostToDevice, h->copy_in));
+        }
         CUDA_TRY(cudaEventRecord(h->ev_in[cidx], h->copy_in));
         CUDA_TRY(cudaStreamWaitEvent(h->compute, h->ev_in[cidx], 0));
         StepArgs a;
         std::memset(&a, 0, sizeof(a));
         a.env_begin = b;
         a.env_end = e;
-        a.actions = h->h_act;
-        a.ksteps = 1;
+        a.actions = act_dev;
+        a.action_stride = k > 1 ? n : 0;
+        a.ksteps = k;
         a.obs_out = h->h_obs;
         a.reward_out = h->h_rew;
         a.done_out = h->h_done;
         a.term_out = term_host ? h->h_term : nullptr;
+        a.steps_out = steps_host ? h->h_steps : nullptr;
         a.flags = flags;
         a.reverse = rev;
+        if (k > 1 && h->kq_entries && (flags & BOATENV_AUTO_RESET)) {
+            a.kq_entries = h->kq_entries;
+            a.kq_counts = h->kq_counts;
+            a.kq_total = h->kq_total;
+        }
         CUDA_TRY(h->precision == 32 ? launch_step_f32(h->cfg, a, h->compute) : launch_step_f64(h->cfg, a, h->compute));
         CUDA_TRY(cudaEventRecord(h->ev_k[cidx], h->compute));
         CUDA_TRY(cudaStreamWaitEvent(h->copy_out, h->ev_k[cidx], 0));
@@ -538,6 +611,8 @@ static int step_host_impl(boatenv_t h, const void *actions_host, void *obs_host,
                                  cudaMemcpyDeviceToHost, h->copy_out));
         CUDA_TRY(cudaMemcpyAsync(done_host + b, h->h_done + b, cnt, cudaMemcpyDeviceToHost, h->copy_out));
         if (term_host) CUDA_TRY(cudaMemcpyAsync(term_host + b, h->h_term + b, cnt, cudaMemcpyDeviceToHost, h->copy_out));
+        if (steps_host)
+            CUDA_TRY(cudaMemcpyAsync(steps_host + b, h->h_steps + b, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, h->copy_out));
     }
     CUDA_TRY(cudaStreamSynchronize(h->copy_out));
     return BOATENV_OK;
@@ -545,7 +620,7 @@ static int step_host_impl(boatenv_t h, const void *actions_host, void *obs_host,
 
 int boatenv_get_field(boatenv_t h, int field, void *out, void *stream) {
     if (!h || !out || field < 0 || field > BOATENV_F_EPISODE) return BOATENV_EINVAL;
-    CUDA_TRY(cudaSetDevice(h->device));
+    GUARD_DEVICE(h);
     CUDA_TRY(h->precision == 32 ? launch_get_field_f32(h->cfg, field, out, (cudaStream_t)stream)
                                 : launch_get_field_f64(h->cfg, field, out, (cudaStream_t)stream));
     return BOATENV_OK;
@@ -553,7 +628,7 @@ int boatenv_get_field(boatenv_t h, int field, void *out, void *stream) {
 
 int boatenv_set_field(boatenv_t h, int field, const void *in, void *stream) {
     if (!h || !in || field < 0 || field > BOATENV_F_EPISODE) return BOATENV_EINVAL;
-    CUDA_TRY(cudaSetDevice(h->device));
+    GUARD_DEVICE(h);
     CUDA_TRY(h->precision == 32 ? launch_set_field_f32(h->cfg, field, in, (cudaStream_t)stream)
                                 : launch_set_field_f64(h->cfg, field, in, (cudaStream_t)stream));
     return BOATENV_OK;
@@ -562,7 +637,7 @@ int boatenv_set_field(boatenv_t h, int field, const void *in, void *stream) {
 int boatenv_env_state_host(boatenv_t h, int64_t env_index, double *out_host) {
     if (!h || !out_host || env_index < 0 || env_index >= h->cfg.n_envs) return BOATENV_EINVAL;
     if (!h->was_reset) return BOATENV_ESTATE;
-    CUDA_TRY(cudaSetDevice(h->device));
+    GUARD_DEVICE(h);
     int rc = ensure_host_path(h);
     if (!rc) rc = ensure_zero_copy(h);
     if (rc) return rc;
@@ -580,14 +655,14 @@ int boatenv_wind_length(boatenv_t h) { return h ? h->cfg.L : BOATENV_EINVAL; }
 int boatenv_wind_table(boatenv_t h, int64_t env_index, double *wv, double *wa, void *stream) {
     if (!h || !wv || !wa || env_index < 0 || env_index >= h->cfg.n_envs) return BOATENV_EINVAL;
     if (!h->was_reset) return BOATENV_ESTATE;
-    CUDA_TRY(cudaSetDevice(h->device));
+    GUARD_DEVICE(h);
     CUDA_TRY(launch_wind_table(h->cfg, env_index, wv, wa, (cudaStream_t)stream));
     return BOATENV_OK;
 }
 
 int boatenv_set_episode_draws(boatenv_t h, const int32_t *s_y_start, const double *knots, void *stream) {
     if (!h) return BOATENV_EINVAL;
-    CUDA_TRY(cudaSetDevice(h->device));
+    GUARD_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)h->cfg.n_envs;
     if (s_y_start) {
@@ -620,6 +695,27 @@ int boatenv_episode_draws_host(const boatenv_params *params, uint64_t seed, int6
     return BOATENV_OK;
 }
 
+int boatenv_episode_draws_batch_host(const boatenv_params *params, uint64_t seed, const int64_t *global_env_ids,
+                                     int64_t n_ids, uint32_t episode_begin, int32_t n_episodes,
+                                     int32_t *s_y_start_out, double *knots_out) {
+    if (!params || !global_env_ids || n_ids < 0 || n_episodes < 0) return BOATENV_EINVAL;
+    DevCfg c;
+    int rc = derive_config(params, c);
+    if (rc) return rc;
+    if (2 * c.fp > 32) return BOATENV_EUNSUPPORTED;
+    for (int32_t e = 0; e < n_episodes; ++e)
+        for (int64_t j = 0; j < n_ids; ++j) {
+            const int64_t g = global_env_ids[j];
+            if (g < 0) return BOATENV_EINVAL;
+            const size_t o = (size_t)e * (size_t)n_ids + (size_t)j;
+            if (s_y_start_out) s_y_start_out[o] = episode_s_y_start(seed, g, episode_begin + (uint32_t)e, c.s_y_half);
+            if (knots_out)
+                for (int t = 0; t < 2 * c.fp; ++t)
+                    knots_out[o * 2 * c.fp + t] = episode_knot(seed, g, episode_begin + (uint32_t)e, t);
+        }
+    return BOATENV_OK;
+}
+
 static size_t state_block_bytes(boatenv_t h) { return (size_t)num_blocks(h->cfg.n_envs) * (size_t)h->cfg.block_bytes; }
 static size_t counter_bytes() { return (size_t)kCounterSlots * 32 * sizeof(double); }
 
@@ -630,7 +726,7 @@ int64_t boatenv_state_bytes(boatenv_t h) {
 int boatenv_export_state(boatenv_t h, void *blob_out, void *stream) {
     if (!h || !blob_out) return BOATENV_EINVAL;
     if (!h->was_reset) return BOATENV_ESTATE;
-    CUDA_TRY(cudaSetDevice(h->device));
+    GUARD_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpyAsync(blob_out, h->cfg.state, state_block_bytes(h), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemcpyAsync((char *)blob_out + state_block_bytes(h), h->cfg.counters, counter_bytes(),
@@ -640,7 +736,7 @@ int boatenv_export_state(boatenv_t h, void *blob_out, void *stream) {
 
 int boatenv_import_state(boatenv_t h, const void *blob_in, void *stream) {
     if (!h || !blob_in) return BOATENV_EINVAL;
-    CUDA_TRY(cudaSetDevice(h->device));
+    GUARD_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpyAsync(h->cfg.state, blob_in, state_block_bytes(h), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->cfg.counters, (const char *)blob_in + state_block_bytes(h), counter_bytes(),
@@ -651,7 +747,7 @@ int boatenv_import_state(boatenv_t h, const void *blob_in, void *stream) {
 
 int boatenv_reduce_counters(boatenv_t h, double *out_device, void *stream) {
     if (!h || !out_device) return BOATENV_EINVAL;
-    CUDA_TRY(cudaSetDevice(h->device));
+    GUARD_DEVICE(h);
     CUDA_TRY(launch_reduce_counters(h->cfg.counters, out_device, (cudaStream_t)stream));
     return BOATENV_OK;
 }
@@ -668,7 +764,7 @@ int boatenv_get_counters(boatenv_t h, double *out_host, void *stream) {
 
 int boatenv_fill_uniform_actions(boatenv_t h, uint64_t step_counter, double scale, void *actions_out, void *stream) {
     if (!h || !actions_out) return BOATENV_EINVAL;
-    CUDA_TRY(cudaSetDevice(h->device));
+    GUARD_DEVICE(h);
     CUDA_TRY(h->precision == 32 ? launch_fill_actions_f32(h->cfg, step_counter, scale, actions_out, (cudaStream_t)stream)
                                 : launch_fill_actions_f64(h->cfg, step_counter, scale, actions_out, (cudaStream_t)stream));
     return BOATENV_OK;

@@ -31,22 +31,22 @@ __global__ void __launch_bounds__(kTile) boat_reset_kernel(const __grid_constant
         const uint32_t e_epi = episode;   // the lane that owns env `src` (the only one that enters below)
         if (lane == src) {
             T d[D_COUNT], wa[4], wb[4], obs[kObsDim];
-#pragma unroll
-            for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
-            const T sy0 = (T)episode_start_y(c, i, e_epi);  // boat_env.py:166-167
-            d[D_SY] = sy0;
+            const int sy0 = episode_start_y(c, i, e_epi);  // boat_env.py:166-167
+            Fx<T> fx;
+            fx.start(c, d, sy0);
+            fx.pack(d);
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 wa[m] = c.ncurves > 0 ? (T)scratch_s[warp][m] : (T)0;
                 wb[m] = c.ncurves > 0 ? (T)scratch_s[warp][4 + m] : (T)0;
             }
             store_vecs<T, D_COUNT>(block_section(c, i, 0), lane, d);
-            *index_ptr(c, i) = 0u;
+            *index_ptr(c, i) = fx.index_word(0);
             *episode_ptr(c, i) = e_epi;
             if (c.ncurves >= 1) store_vecs<T, 4>(block_section(c, i, c.off_wa), lane, wa);
             if (c.ncurves >= 2) store_vecs<T, 4>(block_section(c, i, c.off_wb), lane, wb);
             if (obs_out) {
-                stage_reset_obs<T>(c, obs, sy0);
+                stage_reset_obs<T>(c, obs, (T)sy0);
 #pragma unroll
                 for (int q = 0; q < kObsDim; ++q) obs_out[i * kObsDim + q] = obs[q];
             }
@@ -135,14 +135,54 @@ __device__ __forceinline__ T *dyn_scalar(const DevCfg &c, long long i, int field
     return reinterpret_cast<T *>(block_section(c, i, 0)) + ((field / W) * 32 + (int)(i & 31)) * W + (field % W);
 }
 
+// Field access decodes / encodes the fixed-point carriers of the fp32 mode (struct Fx<float>, common.cuh):
+// rudder_angle, s_x and s_y are exchanged as plain numbers (rounded to T on the way out).
+__device__ __forceinline__ double read_field(const DevCfg &c, long long i, int field, double) {
+    return *dyn_scalar<double>(c, i, field);
+}
+__device__ __forceinline__ double read_field(const DevCfg &c, long long i, int field, float) {
+    const float raw = *dyn_scalar<float>(c, i, field);
+    if (field == D_RUDDER) {
+        const long long rud = ((long long)__float_as_int(raw) << kRudLoBits) | (long long)(*index_ptr(c, i) >> kIndexBits);
+        return (double)rud * (1.0 / 4398046511104.0);
+    }
+    if (field == D_SX) return (double)__float_as_int(raw) * (double)c.f.sx_inv;
+    if (field == D_SY) return (double)__float_as_int(raw) * (double)c.f.sy_inv;
+    return (double)raw;
+}
+__device__ __forceinline__ void write_field(const DevCfg &c, long long i, int field, double v, double) {
+    *dyn_scalar<double>(c, i, field) = v;
+}
+__device__ __forceinline__ int fixed_from(double v, int shift) {
+    const double x = rint(v * (double)(1 << shift));
+    return x >= 2147483647.0 ? 2147483647 : (x <= -2147483648.0 ? (int)0x80000000 : (int)x);
+}
+__device__ __forceinline__ void write_field(const DevCfg &c, long long i, int field, double v, float) {
+    float *p = dyn_scalar<float>(c, i, field);
+    if (field == D_RUDDER) {
+        double x = rint(v * 4398046511104.0);
+        x = fmin(fmax(x, -(double)kRudLimit), (double)kRudLimit);
+        const long long rud = (long long)x;
+        *p = __int_as_float((int)(rud >> kRudLoBits));
+        uint32_t *ix = index_ptr(c, i);
+        *ix = (*ix & kIndexMask) | (((uint32_t)rud & ((1u << kRudLoBits) - 1u)) << kIndexBits);
+    } else if (field == D_SX) {
+        *p = __int_as_float(fixed_from(v, c.f.sx_shift));
+    } else if (field == D_SY) {
+        *p = __int_as_float(fixed_from(v, c.f.sy_shift));
+    } else {
+        *p = (float)v;
+    }
+}
+
 template <typename T>
 __global__ void boat_get_field_kernel(const __grid_constant__ DevCfg c, int field, void *out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n_envs) return;
     if (field < D_COUNT) {
-        reinterpret_cast<T *>(out)[i] = *dyn_scalar<T>(c, i, field);
+        reinterpret_cast<T *>(out)[i] = (T)read_field(c, i, field, T());
     } else {
-        reinterpret_cast<uint32_t *>(out)[i] = (field == BOATENV_F_STEP_INDEX) ? *index_ptr(c, i) : *episode_ptr(c, i);
+        reinterpret_cast<uint32_t *>(out)[i] = (field == BOATENV_F_STEP_INDEX) ? (*index_ptr(c, i) & kIndexMask) : *episode_ptr(c, i);
     }
 }
 
@@ -151,10 +191,15 @@ __global__ void boat_set_field_kernel(const __grid_constant__ DevCfg c, int fiel
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.n_envs) return;
     if (field < D_COUNT) {
-        *dyn_scalar<T>(c, i, field) = reinterpret_cast<const T *>(in)[i];
+        write_field(c, i, field, (double)reinterpret_cast<const T *>(in)[i], T());
     } else {
         const uint32_t x = reinterpret_cast<const uint32_t *>(in)[i];
-        if (field == BOATENV_F_STEP_INDEX) *index_ptr(c, i) = x; else *episode_ptr(c, i) = x;
+        if (field == BOATENV_F_STEP_INDEX) {
+            uint32_t *ix = index_ptr(c, i);
+            *ix = (*ix & ~kIndexMask) | (x & kIndexMask);   // the bits above the index belong to the rudder (fp32 mode)
+        } else {
+            *episode_ptr(c, i) = x;
+        }
     }
 }
 
@@ -164,8 +209,8 @@ template <typename T>
 __global__ void boat_env_state_kernel(const __grid_constant__ DevCfg c, long long i, double *out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
 #pragma unroll
-    for (int f = 0; f < D_COUNT; ++f) out[f] = (double)*dyn_scalar<T>(c, i, f);
-    out[BOATENV_F_STEP_INDEX] = (double)*index_ptr(c, i);
+    for (int f = 0; f < D_COUNT; ++f) out[f] = read_field(c, i, f, T());
+    out[BOATENV_F_STEP_INDEX] = (double)(*index_ptr(c, i) & kIndexMask);
     out[BOATENV_F_EPISODE] = (double)*episode_ptr(c, i);
 }
 

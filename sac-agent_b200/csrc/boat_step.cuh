@@ -63,8 +63,8 @@ __device__ __forceinline__ void fast_sincosf(float x, float &s, float &c) {
 // the reward and the termination code.
 // ---------------------------------------------------------------------------------
 template <int WK>
-__device__ __forceinline__ void substep(const DevCfg &c, double (&d)[D_COUNT], int index, double action, double w,
-                                        double th, double (&acc)[3], double &reward, int &code) {
+__device__ __forceinline__ void substep(const DevCfg &c, double (&d)[D_COUNT], Fx<double> &, int index, double action,
+                                        double w, double th, double (&acc)[3], double &reward, int &code) {
     // fp64 validation mode: the reference's own operation order (Python's a*b*c is
     // (a*b)*c); this translation unit is built with -fmad=false.
     const boatenv_params &p = c.p;
@@ -137,16 +137,24 @@ __device__ __forceinline__ void substep(const DevCfg &c, double (&d)[D_COUNT], i
 }
 
 template <int WK>
-__device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], int index, float action, float w,
-                                        float th, float (&acc)[3], float &reward, int &code) {
+__device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], Fx<float> &fx, int index, float action,
+                                        float w, float th, float (&acc)[3], float &reward, int &code) {
     // fp32 production mode: config products folded on the host (FastConsts); the
     // sqrt/atan2/sin/cos chain of get_kinematics collapses algebraically:
     //   sin(atan2(vx,vy) - s_r) * |v| = vx cos(s_r) - vy sin(s_r)
     //   cos(atan2(vx,vy) - s_r) * |v| = vy cos(s_r) + vx sin(s_r)
+    // Everything a threshold is applied to after ACCUMULATION is carried exactly (struct Fx, common.cuh):
+    // the rudder in 2^-42 rad units (boat_env.py:72-73 is a sum of action / 10 terms), s_x and s_y in fixed point.
     const FastConsts &f = c.f;
     const bool first = (index == 0);
-    float rudder = d[D_RUDDER];
-    if (c.test_mode == 0) rudder = fmaf(action, f.tenth, rudder);
+    if (c.test_mode == 0) {  // rudder += action / 10 (boat_env.py:72-73); |action| is nominally <= 1 and not clipped
+        const float a_c = fminf(fmaxf(action, -64.0f), 64.0f);
+        fx.rud += __double2ll_rn((double)a_c * (4398046511104.0 / 10.0));
+    }
+    const long long rud_abs = fx.rud < 0 ? -fx.rud : fx.rud;
+    const bool rud_broken = rud_abs > f.rud_pi3, rud_penalty = rud_abs > f.rud_pi4;
+    if (rud_abs > kRudLimit) fx.rud = fx.rud < 0 ? -kRudLimit : kRudLimit;  // saturate (only a boat already broken gets here)
+    const float rudder = fx.rudder_view();
     float v_x = d[D_VX], v_y = d[D_VY], v_r = d[D_VR];
 
     float F_Wx = 0.0f, F_Wy = 0.0f;
@@ -179,21 +187,23 @@ __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], in
     const float s_r = fmaf(v_r, f.dt, d[D_SR]);
     float sr, cr;
     fast_sincosf(s_r, sr, cr);
-    const float s_x = fmaf(fmaf(v_x, cr, -v_y * sr), f.dt, d[D_SX]);
-    const float s_y = fmaf(fmaf(v_y, cr, v_x * sr), f.dt, d[D_SY]);
+    fx.sx = add_sat_s32(fx.sx, __float2int_rn(fmaf(v_x, cr, -v_y * sr) * f.sx_k));
+    fx.sy = add_sat_s32(fx.sy, __float2int_rn(fmaf(v_y, cr, v_x * sr) * f.sy_k));
+    const float s_x = (float)fx.sx * f.sx_inv;
+    const float s_y = (float)fx.sy * f.sy_inv;
     const float ay = fabsf(s_y);
     float r = -__fdividef(ay * f.rew_inv_W, 1.0f + __expf(f.rew_k * (ay - f.rew_y0)));
     // termination cascade boat_env.py:84-105, lowest priority first (later selects override);
     // fuel < 0 (:94) and t_max <= t (:98) depend on the step count only: integer thresholds
     const float ar = fabsf(rudder);
-    const bool goal = s_x >= f.goal;
-    code = (ar > f.pi3) ? BOATENV_TERM_RUDDER_BROKEN : BOATENV_TERM_NONE;
+    const bool goal = fx.sx >= f.sx_goal;
+    code = rud_broken ? BOATENV_TERM_RUDDER_BROKEN : BOATENV_TERM_NONE;
     code = (index + 1 >= c.timeout_steps) ? BOATENV_TERM_TIMEOUT : code;
     code = (index + 1 >= c.fuel_steps) ? BOATENV_TERM_OUT_OF_FUEL : code;
-    code = (ay > f.oob || s_x < 0.0f) ? BOATENV_TERM_OUT_OF_BOUNDS : code;
+    code = (fx.sy > f.sy_oob || fx.sy < -f.sy_oob || fx.sx < 0) ? BOATENV_TERM_OUT_OF_BOUNDS : code;
     code = goal ? BOATENV_TERM_REACHED_GOAL : code;
     r += goal ? 1000.0f : 0.0f;
-    if (ar > f.pi4) r = fmaf(-100.0f, ar, r);
+    if (rud_penalty) r = fmaf(-100.0f, ar, r);
     if (fabsf(s_r) > f.pi2) r -= 1.0f;
     reward = r;
 
@@ -552,25 +562,35 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
         if (WK == WIND_BOTH) load_vecs<T, 4>(reinterpret_cast<const char *>(sb) + c.off_wb, lane, wb);
         const uint32_t epi_s = KMULTI ? reinterpret_cast<const uint32_t *>(sb + c.off_epi)[lane] : 0u;
         const uint32_t ixw = reinterpret_cast<const uint32_t *>(sb + c.off_idx)[lane];
-        int index = (int)ixw;
+        int index;
+        Fx<T> fx;                     // fp32 mode: exact rudder / position carriers decoded from their slots
+        fx.load(c, d, ixw, index);
         uint32_t episode_k = epi_s;   // K > 1 only: this launch's view of the env's episode number
         // The refill below overwrites this stage, so it must not be issued before EVERY lane's loads of the stage
         // have returned (issuing them is not enough: a refill served from L2 can land within a few hundred
         // cycles).  The vote consumes a register of each of the loads above in every lane -- the compiler is free
         // to order them, so all of them take part -- and lane 0's block number depends on the vote: a true
-        // dependency for the hardware scoreboard.  The predicate is never true: a step index never reaches the
-        // poison value (indices stay below 2^20), no arithmetic produces the poison NaN, and the 0xFF fill of the
-        // padding lanes of a ragged last block is not the poison pattern either.
-        bool never = ixw == 0x7fc00001u || (KMULTI && epi_s == 0x7fc00001u && ixw == 0x7fc00002u);
+        // dependency for the hardware scoreboard.  The predicate is never true: a step index never reaches
+        // 2^20 - 1 (L <= 2^20 - 64, checked at create), no arithmetic produces the poison NaN, and the inspected
+        // registers are genuine floating-point slots (fp32 mode: v_r and s_r; the rudder / position slots hold
+        // fixed-point bit patterns and are not looked at).  The padding lanes of a ragged last block read the
+        // 0xFF fill, whose index field IS the pattern: they are excluded (their loads still complete before the
+        // vote, a lane's instructions issue in order).
+        bool never = ((ixw & kIndexMask) == kIndexMask && active) || (KMULTI && epi_s == 0x7fc00001u && (ixw & kIndexMask) == kIndexMask - 1u);
         constexpr int W = VecOf<T>::W;   // one register of every 16-byte vector load
+        constexpr int kProbe = sizeof(T) == 4 ? 2 : 0;
 #pragma unroll
-        for (int v = 0; v < D_COUNT / W; ++v) never |= is_poison(d[v * W]);
+        for (int v = 0; v < D_COUNT / W; ++v) never |= is_poison(d[v * W + kProbe]);
 #pragma unroll
         for (int v = 0; v < 4 / W; ++v) {
             if (kCurves) never |= is_poison(wa[v * W]);
             if (WK == WIND_BOTH) never |= is_poison(wb[v * W]);
         }
+#ifdef BOAT_DEBUG_NO_REFILL_VOTE  // ablation only (profiles/r02_refill_vote_ablation.txt): the benchmark-regime parity tests must fail
+        const unsigned never_mask = 0u;
+#else
         const unsigned never_mask = __ballot_sync(FULL, never);
+#endif
         if (lane == 0) {
             // The stage is consumed: refill it kStages blocks ahead.
             const int q = seq + kStages * wstride + (never_mask != 0u ? 1 : 0);
@@ -593,12 +613,21 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
         bool ring_in_flight = false;
         char *gb = c.state + (size_t)blk * (size_t)bb;
 
+        // the carried scalars + step index of this lane's env -> its block in HBM (fp32 mode: d[] keeps the float
+        // views of rudder / s_x / s_y that stage_obs() reads; a copy gets the fixed-point bit patterns)
+        auto store_dyn = [&]() {
+            T dd[D_COUNT];
+#pragma unroll
+            for (int q = 0; q < D_COUNT; ++q) dd[q] = d[q];
+            fx.pack(dd);
+            store_vecs<T, D_COUNT>(gb, lane, dd);
+            st_state(reinterpret_cast<uint32_t *>(gb + c.off_idx) + lane, fx.index_word(index));
+        };
         // state + per-env outputs of this launch (K = 1: right after the sub-step; K > 1: after the loop)
         auto store_results = [&]() {
             if (active) {
 #ifndef BOAT_DEBUG_SKIP_STATE
-                store_vecs<T, D_COUNT>(gb, lane, d);
-                st_state(reinterpret_cast<uint32_t *>(gb + c.off_idx) + lane, (uint32_t)index);
+                store_dyn();
 #endif
                 if (KMULTI && wind_dirty) {  // wind coefficients change only on the slow path
                     if (kCurves) store_vecs<T, 4>(gb + c.off_wa, lane, wa);
@@ -653,7 +682,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
 #ifdef BOAT_DEBUG_NOCOMPUTE  // memory-pattern experiment only: stream the state through untouched
                 acc[0] = acc[1] = acc[2] = w + th; rew = action; code = BOATENV_TERM_NONE;
 #else
-                substep<WK>(c, d, index, action, w, th, acc, rew, code);
+                substep<WK>(c, d, fx, index, action, w, th, acc, rew, code);
 #endif
                 rsum += rew;
                 ++nsteps;
@@ -753,11 +782,10 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                         queue_push(queue, rq);
 #endif
                         if (is_done) {  // Boat.__init__  boat_env.py:144-201
-#pragma unroll
-                            for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
+                            fx.start(c, d, 0);
+                            index = 0;
                             stage_reset_obs<T>(c, row, (T)0);  // only experiment 2 starts off the centre line (:166-167)
-                            store_vecs<T, D_COUNT>(gb, lane, d);
-                            st_state(reinterpret_cast<uint32_t *>(gb + c.off_idx) + lane, 0u);
+                            store_dyn();
                             *epi_g = rq.episode;
                         }
                     }
@@ -769,8 +797,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                     // only the cheap part of Boat.__init__ (boat_env.py:144-201) here
                     const unsigned pos = atomicAdd(kq_cnt, 1u);
                     a.kq_entries[(size_t)blockIdx.x * a.kq_cap + pos] = make_uint2((unsigned)i, episode + 1u);
-#pragma unroll
-                    for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
+                    fx.start(c, d, 0);
                     index = 0;
                     episode += 1u;
                     *epi_g = episode;
@@ -802,19 +829,14 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                             }
                         }
                         if (e_done) {  // Boat.__init__  boat_env.py:144-201
-#pragma unroll
-                            for (int q = 0; q < D_COUNT; ++q) d[q] = (T)0;
-                            const T sy0 = (T)episode_start_y(c, i, e_epi);  // :166-167
-                            d[D_SY] = sy0;
+                            const int sy0 = episode_start_y(c, i, e_epi);  // :166-167
+                            fx.start(c, d, sy0);
                             index = 0;
                             episode = e_epi;
                             episode_k = e_epi;
                             *epi_g = e_epi;
-                            stage_reset_obs<T>(c, row, sy0);
-                            if (!KMULTI) {
-                                store_vecs<T, D_COUNT>(gb, lane, d);
-                                st_state(reinterpret_cast<uint32_t *>(gb + c.off_idx) + lane, 0u);
-                            }
+                            stage_reset_obs<T>(c, row, (T)sy0);
+                            if (!KMULTI) store_dyn();
                         }
                     }
                     __syncwarp();  // scratch is reused by the next env of this warp

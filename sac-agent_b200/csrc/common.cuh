@@ -56,6 +56,13 @@ struct FastConsts {
     float fuel0, goal, oob, pi3, pi4, pi2;
     float rew_inv_W, rew_k, rew_y0;     // reward_functions.py:52-54
     float inv_Lm1;                      // 1 / (L - 1): wind sample index -> local spline coordinate
+    // exact carriers of the fp32 mode (struct Fx<float> below): fixed-point positions and rudder
+    float sx_k, sy_k;                   // dt * 2^sx_shift, dt * 2^sy_shift: position increment -> fixed-point units
+    float sx_inv, sy_inv;               // 2^-sx_shift, 2^-sy_shift
+    int sx_shift, sy_shift;
+    int sx_goal;                        // s_x >= goal_line        <=> sx >= sx_goal   (boat_env.py:85)
+    int sy_oob;                         // abs(s_y) > W + offset   <=> |sy| > sy_oob   (boat_env.py:90)
+    long long rud_pi3, rud_pi4;         // abs(rudder) > pi/3, pi/4 <=> |rud| > rud_pi3, rud_pi4 (boat_env.py:102,107)
 };
 
 struct DevCfg {
@@ -191,7 +198,70 @@ template <typename T> struct VecOf;
 template <> struct VecOf<float> { using type = float4; static constexpr int W = 4; };
 template <> struct VecOf<double> { using type = double2; static constexpr int W = 2; };
 
+// ---------------------------------------------------------------------------------
+// Exact carriers of the fp32 production mode.  The termination cascade (boat_env.py:84-105) and the rudder
+// penalty (:107) compare ACCUMULATED quantities with thresholds; accumulated in fp32 they drift by ~1e-6 (rudder)
+// / ~5e-3 m (s_x) and flip a threshold one step early or late in ~1e-4 of the episodes.  So the fp32 mode carries
+//   rudder  as a 44-bit fixed-point number, 2^-42 rad per unit, range +-2 rad (saturating): the upper 32 bits
+//           sit in the D_RUDDER slot of the state, the lower 12 in bits 20..31 of the step-index word.  The
+//           rudder depends on the actions only, so it stays within ~2e-12 rad of the reference's fp64 sum.
+//   s_x,s_y as int32 fixed-point numbers (2^-19 m / 2^-21 m for the reference track, saturating) in their slots.
+// No extra bytes per env.  The fp64 validation mode carries plain doubles (Fx<double> is empty).
+// ---------------------------------------------------------------------------------
+constexpr int kRudShift = 42;            // rudder units per rad = 2^42
+constexpr int kRudLoBits = 12;           // low bits of the rudder stored beside the step index
+constexpr int kIndexBits = 20;           // step index: bits 0..19 of the index word (L <= 2^20 - 64)
+constexpr uint32_t kIndexMask = (1u << kIndexBits) - 1u;
+constexpr long long kRudLimit = (1LL << 43) - 1;   // |rudder| saturates just below 2 rad
+
 #ifdef __CUDACC__
+__device__ __forceinline__ int add_sat_s32(int a, int b) {
+    int r;
+    asm("add.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
+template <typename T> struct Fx;
+template <> struct Fx<double> {
+    __device__ __forceinline__ void load(const DevCfg &, const double (&)[D_COUNT], uint32_t ixw, int &index) { index = (int)(ixw & kIndexMask); }
+    __device__ __forceinline__ void pack(double (&)[D_COUNT]) const {}
+    __device__ __forceinline__ uint32_t index_word(int index) const { return (uint32_t)index; }
+    __device__ __forceinline__ void start(const DevCfg &, double (&d)[D_COUNT], int s_y0) {  // Boat.__init__ boat_env.py:144-201
+#pragma unroll
+        for (int q = 0; q < D_COUNT; ++q) d[q] = 0.0;
+        d[D_SY] = (double)s_y0;
+    }
+};
+template <> struct Fx<float> {
+    long long rud;
+    int sx, sy;
+    __device__ __forceinline__ void load(const DevCfg &, const float (&d)[D_COUNT], uint32_t ixw, int &index) {
+        index = (int)(ixw & kIndexMask);
+        rud = (long long)(((unsigned long long)(long long)__float_as_int(d[D_RUDDER]) << kRudLoBits) |
+                          (unsigned long long)(ixw >> kIndexBits));
+        sx = __float_as_int(d[D_SX]);
+        sy = __float_as_int(d[D_SY]);
+    }
+    // the bit patterns that go to HBM (d keeps its float views; call on a copy or right before the store)
+    __device__ __forceinline__ void pack(float (&d)[D_COUNT]) const {
+        d[D_RUDDER] = __int_as_float((int)(rud >> kRudLoBits));
+        d[D_SX] = __int_as_float(sx);
+        d[D_SY] = __int_as_float(sy);
+    }
+    __device__ __forceinline__ uint32_t index_word(int index) const {
+        return (uint32_t)index | (((uint32_t)rud & ((1u << kRudLoBits) - 1u)) << kIndexBits);
+    }
+    __device__ __forceinline__ float rudder_view() const { return (float)(int)(rud >> kRudLoBits) * 9.31322574615478515625e-10f; }  // 2^-30
+    __device__ __forceinline__ void start(const DevCfg &c, float (&d)[D_COUNT], int s_y0) {
+#pragma unroll
+        for (int q = 0; q < D_COUNT; ++q) d[q] = 0.0f;
+        d[D_SY] = (float)s_y0;
+        rud = 0;
+        sx = 0;
+        sy = s_y0 * (1 << c.f.sy_shift);   // |s_y0| <= 0.8 W: no overflow (the shift leaves room for W + offset)
+    }
+};
+
 __device__ __forceinline__ void unpack(const float4 &v, float *o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 __device__ __forceinline__ void unpack(const double2 &v, double *o) { o[0] = v.x; o[1] = v.y; }
 __device__ __forceinline__ float4 pack(const float *o) { return make_float4(o[0], o[1], o[2], o[3]); }

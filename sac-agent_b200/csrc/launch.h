@@ -3,6 +3,30 @@
 #pragma once
 #include "common.cuh"
 
+// Every handle-based entry point runs on the handle's device and restores the caller's current device on return
+// (a multi-GPU process keeps torch's current device untouched).
+namespace boatenv {
+class DeviceGuard {
+public:
+    explicit DeviceGuard(int device) : prev_(-1), err_(cudaSuccess) {
+        err_ = cudaGetDevice(&prev_);
+        if (err_ == cudaSuccess && prev_ != device) err_ = cudaSetDevice(device); else if (err_ == cudaSuccess) prev_ = -1;
+    }
+    ~DeviceGuard() { if (prev_ >= 0) cudaSetDevice(prev_); }
+    bool ok() const { return err_ == cudaSuccess; }
+    cudaError_t error() const { return err_; }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+private:
+    int prev_;
+    cudaError_t err_;
+};
+}  // namespace boatenv
+#define GUARD_DEVICE(h)                                   \
+    boatenv::DeviceGuard _guard((h)->device);                      \
+    if (!_guard.ok()) return (int)_guard.error()
+
+
 namespace boatenv {
 
 void count_launch();

@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <mutex>
 
 #include "../../include/boatenv.h"
 #include "common.cuh"
@@ -376,19 +377,29 @@ extern "C" int boatagent_policy_act(const void *weight_blob, const float *obs, c
     case 8: kern = policy_mlp_kernel<8>; break;
     default: return BOATENV_EUNSUPPORTED;
     }
-    static int n_sm = 0, configured_dev = -1;
+    // per-device configuration (max dynamic shared memory of the four instantiations, SM count): done once per
+    // device under a mutex, so that alternating devices or host threads neither thrash nor race
+    static std::mutex mu;
+    static int n_sm_of[64] = {0};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
-    if (configured_dev != dev) {
-        for (kern_t k : {(kern_t)policy_mlp_kernel<1>, (kern_t)policy_mlp_kernel<2>, (kern_t)policy_mlp_kernel<4>,
-                         (kern_t)policy_mlp_kernel<8>}) {
-            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    int n_sm = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (n_sm_of[dev] == 0) {
+            for (kern_t k : {(kern_t)policy_mlp_kernel<1>, (kern_t)policy_mlp_kernel<2>, (kern_t)policy_mlp_kernel<4>,
+                             (kern_t)policy_mlp_kernel<8>}) {
+                e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+                if (e != cudaSuccess) return (int)e;
+            }
+            int v = 0;
+            e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
             if (e != cudaSuccess) return (int)e;
+            n_sm_of[dev] = v;
         }
-        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return (int)e;
-        configured_dev = dev;
+        n_sm = n_sm_of[dev];
     }
     const long long tiles = (n + kTileM - 1) / kTileM;
     const unsigned grid = (unsigned)(tiles < n_sm ? tiles : n_sm);

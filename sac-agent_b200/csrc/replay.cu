@@ -199,7 +199,8 @@ int boatreplay_create(int64_t max_size, int32_t obs_dim, int32_t n_actions, int 
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return BOATENV_ENODEVICE;
-    CUDA_TRY(cudaSetDevice(device));
+    boatenv::DeviceGuard _guard(device);
+    if (!_guard.ok()) return (int)_guard.error();
     boatreplay_handle *r = new (std::nothrow) boatreplay_handle();
     if (!r) return BOATENV_EINVAL;
     std::memset(r, 0, sizeof(*r));
@@ -230,7 +231,7 @@ int boatreplay_create(int64_t max_size, int32_t obs_dim, int32_t n_actions, int 
 
 int boatreplay_destroy(boatreplay_t r) {
     if (!r) return BOATENV_EINVAL;
-    cudaSetDevice(r->device);
+    boatenv::DeviceGuard _guard(r->device);
     cudaFree(r->state);
     cudaFree(r->new_state);
     cudaFree(r->action);
@@ -244,7 +245,7 @@ int boatreplay_store(boatreplay_t r, int64_t n, const void *s, const void *a, co
                      const uint8_t *done, void *stream) {
     if (!r || n < 0 || !s || !a || !rew || !s2 || !done) return BOATENV_EINVAL;
     if (n == 0) return BOATENV_OK;
-    CUDA_TRY(cudaSetDevice(r->device));
+    GUARD_DEVICE(r);
     CUDA_TRY(r->precision == 32 ? launch_store<float>(r, n, s, a, rew, s2, done, (cudaStream_t)stream)
                                 : launch_store<double>(r, n, s, a, rew, s2, done, (cudaStream_t)stream));
     r->mem_cntr += n;  // buffer.py:22
@@ -255,7 +256,7 @@ int boatreplay_sample(boatreplay_t r, int64_t batch, uint64_t seed, uint64_t cou
                       void *r_out, void *s2_out, uint8_t *done_out, int64_t *idx_out, void *stream) {
     if (!r || batch <= 0 || !s_out || !a_out || !r_out || !s2_out || !done_out) return BOATENV_EINVAL;
     if (r->mem_cntr <= 0) return BOATENV_ESTATE;  // np.random.choice(0, n) raises ValueError
-    CUDA_TRY(cudaSetDevice(r->device));
+    GUARD_DEVICE(r);
     CUDA_TRY(r->precision == 32
                  ? launch_gather<float>(r, batch, nullptr, (long long *)idx_out, seed, counter, s_out, a_out, r_out,
                                         s2_out, done_out, (cudaStream_t)stream)
@@ -267,7 +268,7 @@ int boatreplay_sample(boatreplay_t r, int64_t batch, uint64_t seed, uint64_t cou
 int boatreplay_gather(boatreplay_t r, int64_t batch, const int64_t *idx, void *s_out, void *a_out, void *r_out,
                       void *s2_out, uint8_t *done_out, void *stream) {
     if (!r || batch <= 0 || !idx || !s_out || !a_out || !r_out || !s2_out || !done_out) return BOATENV_EINVAL;
-    CUDA_TRY(cudaSetDevice(r->device));
+    GUARD_DEVICE(r);
     CUDA_TRY(r->precision == 32 ? launch_gather<float>(r, batch, (const long long *)idx, nullptr, 0, 0, s_out, a_out,
                                                        r_out, s2_out, done_out, (cudaStream_t)stream)
                                 : launch_gather<double>(r, batch, (const long long *)idx, nullptr, 0, 0, s_out, a_out,
@@ -275,6 +276,11 @@ int boatreplay_gather(boatreplay_t r, int64_t batch, const int64_t *idx, void *s
     return BOATENV_OK;
 }
 
+int boatreplay_set_mem_cntr(boatreplay_t r, int64_t mem_cntr) {
+    if (!r || mem_cntr < 0) return BOATENV_EINVAL;
+    r->mem_cntr = mem_cntr;
+    return BOATENV_OK;
+}
 int64_t boatreplay_mem_cntr(boatreplay_t r) { return r ? r->mem_cntr : BOATENV_EINVAL; }
 int64_t boatreplay_mem_size(boatreplay_t r) { return r ? r->mem_size : BOATENV_EINVAL; }
 
@@ -288,7 +294,7 @@ int boatenv_step_store(boatenv_t h, boatreplay_t r, const void *actions, void *o
         return BOATENV_EINVAL;
     if (c.n_envs > r->mem_size) return BOATENV_EUNSUPPORTED;  // a step must not lap the ring
     if ((reinterpret_cast<uintptr_t>(obs_inout) & 15u) != 0) return BOATENV_EALIGN;
-    CUDA_TRY(cudaSetDevice(r->device));
+    GUARD_DEVICE(r);
     StepArgs a;
     std::memset(&a, 0, sizeof(a));
     a.env_begin = 0;

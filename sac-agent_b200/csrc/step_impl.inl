@@ -1,6 +1,8 @@
 // step_impl.inl -- included by step_f32.cu (REAL=float) and step_f64.cu (REAL=double):
 // instantiates the kernels for one precision and defines its launchers.
 #include <algorithm>
+#include <mutex>
+#include <vector>
 
 #include "aux_kernels.cuh"
 #include "launch.h"
@@ -10,6 +12,9 @@ namespace boatenv {
 #define BOAT_CAT2(a, b) a##b
 #define BOAT_CAT(a, b) BOAT_CAT2(a, b)
 #define FN(name) BOAT_CAT(name, REAL_SUFFIX)
+
+struct OccEntry { int dev, smem, ctas_per_sm, n_sm; };
+constexpr int kMaxDevices = 64;
 
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
@@ -22,19 +27,39 @@ static cudaError_t launch_step_wk(const DevCfg &c, const StepArgs &a_in, cudaStr
     constexpr int n_setup = setup_warps<WK, KMULTI>();
     constexpr int threads = kTile + 32 * n_setup;
     const int smem = CtaSmem<REAL>(c.block_bytes, c.ncurves, c.npieces, n_setup, !KMULTI && a.rp.state != nullptr).bytes;
-    static int cached_smem = -1, ctas_per_sm = 0, n_sm = 0, cached_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cached_smem != smem || cached_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    // Occupancy of this instantiation per (device, shared-memory size): queried once each, kept in a small
+    // mutex-protected table (boatenv_step and boatenv_step_store use the same kernel with different layouts,
+    // several handles / devices / host threads may alternate).
+    int ctas_per_sm = 0, n_sm = 0;
+    {
+        static std::mutex mu;
+        static std::vector<OccEntry> table;
+        static int max_smem_set[kMaxDevices] = {0};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, threads, smem);
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
-        cached_smem = smem;
-        cached_dev = dev;
+        if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+        std::lock_guard<std::mutex> lock(mu);
+        const OccEntry *hit = nullptr;
+        for (const OccEntry &o : table)
+            if (o.dev == dev && o.smem == smem) { hit = &o; break; }
+        if (!hit) {
+            if (smem > max_smem_set[dev]) {  // the attribute is a maximum: raise it, never lower it
+                e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                if (e != cudaSuccess) return e;
+                max_smem_set[dev] = smem;
+            }
+            OccEntry o = {dev, smem, 0, 0};
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o.ctas_per_sm, kern, threads, smem);
+            if (e != cudaSuccess) return e;
+            e = cudaDeviceGetAttribute(&o.n_sm, cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return e;
+            if (o.ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
+            table.push_back(o);
+            hit = &table.back();
+        }
+        ctas_per_sm = hit->ctas_per_sm;
+        n_sm = hit->n_sm;
     }
     const long long nblk = ((a.env_end + 31) >> 5) - (a.env_begin >> 5);
     long long grid = (nblk + kWarpsPerCta - 1) / kWarpsPerCta;

@@ -44,8 +44,9 @@ struct boattoy_handle {
 
 namespace {
 
-template <typename T>
-__device__ __forceinline__ T toy_param(const ToyCfg &c, long long env, int k) {
+// Parameter k of env `env`: the script constant, jittered by Philox for env != 0.  Host and device evaluate the
+// same expression (boattoy_params_host hands the values to a CPU reference).
+__host__ __device__ __forceinline__ double toy_param_value(const ToyCfg &c, long long env, int k) {
     double v = c.params[k];
     if (env != 0 && c.jitter != 0.0) {
         const Philox4 r = philox4x32_10((uint32_t)env, (uint32_t)((unsigned long long)env >> 32), (uint32_t)(k >> 2),
@@ -53,8 +54,10 @@ __device__ __forceinline__ T toy_param(const ToyCfg &c, long long env, int k) {
         const double u = (double)(philox_word(r, k & 3) >> 8) * (1.0 / 8388608.0) - 1.0;
         v = v * (1.0 + c.jitter * u);
     }
-    return (T)v;
+    return v;
 }
+template <typename T>
+__device__ __forceinline__ T toy_param(const ToyCfg &c, long long env, int k) { return (T)toy_param_value(c, env, k); }
 
 // control_blocks.py:16-36 for calls > 0: returns x*dt + last (unclamped), stores clamped.
 template <typename T>
@@ -79,8 +82,12 @@ __global__ void __launch_bounds__(256) toy_car_kernel(const __grid_constant__ To
     uint32_t n = calls[i];
     T angle = s[0], v_last = s[1], s_x = s[2], s_y = s[3], v = (T)0;
     const T inf = (T)__int_as_float(0x7f800000);
+    // fp32 mode: 5000 additions of 0.01 in fp32 would drift by ~1e-4 rad, so the heading is (calls + 1) * dtheta
+    // in fp64 (the reference's accumulated sum equals it to ~1e-13), reduced to [-pi, pi] before the fp32 sincos
+    const double dtheta_d = toy_param_value(c, i, 2);
     for (int it = 0; it < k; ++it) {
-        angle += dtheta;                                              // :23
+        if (sizeof(T) == 8) angle += dtheta;                          // :23
+        else angle = (T)((double)(n + 1u) * dtheta_d);
         if (n == 0) {                                                 // call 0 of all three integrators
             v = (T)0;                                                 // Integrator(upper_limit=10): initial 0
             v_last = (v >= v_limit) ? v_limit : v;
@@ -90,7 +97,13 @@ __global__ void __launch_bounds__(256) toy_car_kernel(const __grid_constant__ To
             v = integrate<T>(accel, dt, v_last, v_limit);             // :24
             T sn, cs;
             if (sizeof(T) == 8) { sn = (T)sin((double)angle); cs = (T)cos((double)angle); }
-            else { float a, b; sincosf((float)angle, &a, &b); sn = (T)a; cs = (T)b; }
+            else {
+                const double ang = (double)(n + 1u) * dtheta_d;
+                const double red = ang - 6.283185307179586476925 * rint(ang * 0.15915494309189533577);
+                float a, b;
+                sincosf((float)red, &a, &b);
+                sn = (T)a; cs = (T)b;
+            }
             T dummy_last = s_x;
             s_x = integrate<T>(v * cs, dt, dummy_last, inf);          // :26,29
             dummy_last = s_y;
@@ -124,23 +137,33 @@ __global__ void __launch_bounds__(256) toy_parachute_kernel(const __grid_constan
     uint32_t word = calls[i];
     bool finished = (word >> 31) != 0;
     uint32_t n = word & 0x7fffffffu;
-    T total_a = s4[0], v_last = s4[1], s_last = s4[2], v = s4[3];
-    T s = (n == 0) ? h0 : s_last;
+    // state slots: {total_a, v (= a_integrator.last: its limits are infinite), height}.  The height s is the sum of
+    // ~2650 increments and decides the stopping iteration (:29), so the fp32 mode carries it in fp64 -- its two
+    // 32-bit halves take slots 2 and 3 (no extra bytes); the fp64 mode keeps {.., s_last, v}.
+    T total_a = s4[0], v_last = s4[1], v = s4[1];
+    double s_acc = sizeof(T) == 8 ? (double)s4[2]
+                                  : __hiloint2double(__float_as_int((float)s4[3]), __float_as_int((float)s4[2]));
+    if (sizeof(T) == 8) v = s4[3];
+    double s_d = (n == 0) ? toy_param_value(c, i, 0) : s_acc;
+    const double h1_d = (double)h1;
     const T inf = (T)__int_as_float(0x7f800000);
     for (int it = 0; it < k && !finished; ++it) {
         total_a -= g;                                                 // :24
-        if (n == 0) { v = (T)0; v_last = v; s = h0; s_last = s; }     // call 0: initial values (:18-19)
+        if (n == 0) { v = (T)0; v_last = v; s_d = sizeof(T) == 8 ? (double)h0 : toy_param_value(c, i, 0); }  // call 0: initial values (:18-19)
         else {
             v = integrate<T>(total_a, dt, v_last, inf);               // :25
-            s = integrate<T>(v, dt, s_last, inf);                     // :26
+            s_d = sizeof(T) == 8 ? (double)((T)v * dt + (T)s_d) : (double)(v * dt) + s_d;   // :26
         }
         ++n;
-        if (s < (T)0) { finished = true; break; }                     // :29-30
-        const T area = (s < h1) ? area_chute : area_free;             // :33-36
+        if (s_d < 0.0) { finished = true; break; }                    // :29-30
+        const T area = (s_d < h1_d) ? area_chute : area_free;         // :33-36
         const T F_w = v * v * (T)0.5 * rho * c_w * area;
         total_a = F_w / mass;                                         // :38
     }
-    s4[0] = total_a; s4[1] = v_last; s4[2] = s_last; s4[3] = v;
+    const T s = (T)s_d;
+    s4[0] = total_a; s4[1] = v_last;
+    if (sizeof(T) == 8) { s4[2] = (T)s_d; s4[3] = v; }
+    else { s4[2] = (T)__int_as_float(__double2loint(s_d)); s4[3] = (T)__int_as_float(__double2hiint(s_d)); }
     store_group<T, 4>(state, c.n_envs, i, s4);
     calls[i] = n | (finished ? 0x80000000u : 0u);
     T o[4] = {s, v, total_a, (T)n};
@@ -163,7 +186,8 @@ int boattoy_create(int kind, int64_t n_envs, const double *params_host, int32_t 
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return BOATENV_ENODEVICE;
-    CUDA_TRY(cudaSetDevice(device));
+    boatenv::DeviceGuard _guard(device);
+    if (!_guard.ok()) return (int)_guard.error();
     boattoy_handle *t = new (std::nothrow) boattoy_handle();
     if (!t) return BOATENV_EINVAL;
     std::memset(t, 0, sizeof(*t));
@@ -186,9 +210,24 @@ int boattoy_create(int kind, int64_t n_envs, const double *params_host, int32_t 
     return boattoy_reset(t, nullptr);
 }
 
+int boattoy_params_host(int kind, const double *params_host, int32_t n_params, double jitter, uint64_t seed,
+                        int64_t env_begin, int64_t n_envs, double *out) {
+    if (!params_host || !out || env_begin < 0 || n_envs < 0) return BOATENV_EINVAL;
+    if (kind != BOATTOY_CAR && kind != BOATTOY_PARACHUTE) return BOATENV_EINVAL;
+    if (n_params != (kind == BOATTOY_CAR ? kCarParams : kParachuteParams)) return BOATENV_EINVAL;
+    ToyCfg c;
+    std::memset(&c, 0, sizeof(c));
+    c.seed = seed;
+    c.jitter = jitter;
+    for (int k = 0; k < n_params; ++k) c.params[k] = params_host[k];
+    for (int64_t e = 0; e < n_envs; ++e)
+        for (int k = 0; k < n_params; ++k) out[e * n_params + k] = toy_param_value(c, env_begin + e, k);
+    return BOATENV_OK;
+}
+
 int boattoy_destroy(boattoy_t t) {
     if (!t) return BOATENV_EINVAL;
-    cudaSetDevice(t->device);
+    boatenv::DeviceGuard _guard(t->device);
     cudaFree(t->state);
     cudaFree(t->calls);
     delete t;
@@ -197,7 +236,7 @@ int boattoy_destroy(boattoy_t t) {
 
 int boattoy_reset(boattoy_t t, void *stream) {
     if (!t) return BOATENV_EINVAL;
-    CUDA_TRY(cudaSetDevice(t->device));
+    GUARD_DEVICE(t);
     CUDA_TRY(cudaMemsetAsync(t->state, 0, (size_t)t->cfg.n_envs * 4 * t->esize, (cudaStream_t)stream));
     CUDA_TRY(cudaMemsetAsync(t->calls, 0, (size_t)t->cfg.n_envs * sizeof(uint32_t), (cudaStream_t)stream));
     return BOATENV_OK;
@@ -206,7 +245,7 @@ int boattoy_reset(boattoy_t t, void *stream) {
 int boattoy_step(boattoy_t t, int32_t k, void *out, uint8_t *done_out, void *stream) {
     if (!t || !out || k < 1) return BOATENV_EINVAL;
     if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return BOATENV_EALIGN;
-    CUDA_TRY(cudaSetDevice(t->device));
+    GUARD_DEVICE(t);
     const unsigned grid = (unsigned)((t->cfg.n_envs + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;
     if (t->kind == BOATTOY_CAR) {

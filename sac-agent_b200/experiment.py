@@ -74,6 +74,10 @@ class Experiment:
     def save_configs(self, config=None):
         """configs/original_config.yaml + the tuned draw as configs/tuned_configs.yaml (:37-41)."""
         cfg = _plain(DEFAULTS if config is None else config)
+        for sec, keys in DEFAULTS.items():   # a partial config still leaves a complete reference-style YAML behind
+            have = cfg.setdefault(sec, {})
+            for k, v in keys.items():
+                have.setdefault(k, v)
         cdir = os.path.join(self.experiment_dir, "configs")
         with open(os.path.join(cdir, "original_config.yaml"), "w") as f:
             yaml.dump(cfg, f, default_flow_style=False)

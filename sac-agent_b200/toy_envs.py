@@ -40,6 +40,7 @@ class _Toy:
         if unknown:
             raise TypeError(f"unknown parameters {sorted(unknown)}")
         self.params = {**self.DEFAULTS, **params}
+        self._jitter, self._seed = float(jitter), int(seed)
         self.n_envs = int(n_envs)
         self.precision = {"fp32": 32, "fp64": 64, 32: 32, 64: 64}[precision]
         self.dtype = torch.float32 if self.precision == 32 else torch.float64
@@ -70,6 +71,18 @@ class _Toy:
 
     def reset(self):
         _lib.check(self._L.boattoy_reset(self._h, self._stream()), "boattoy_reset")
+
+    def env_params(self, env_begin=0, n=None):
+        """The (jittered) parameters envs [env_begin, env_begin + n) run with: float64 [n, len(DEFAULTS)] in the
+        order of ``DEFAULTS`` (host computation, the same Philox expression as the kernels)."""
+        import numpy as np
+        n = self.n_envs - int(env_begin) if n is None else int(n)
+        vals = [float(self.params[k]) for k in self.DEFAULTS]
+        arr = (C.c_double * len(vals))(*vals)
+        out = np.empty((n, len(vals)), dtype=np.float64)
+        _lib.check(self._L.boattoy_params_host(self.KIND, arr, len(vals), self._jitter, self._seed, int(env_begin), n,
+                                               out.ctypes.data), "boattoy_params_host")
+        return out
 
     def step(self, k=1):
         """k loop iterations per env; returns (out[n_envs, 4], done[n_envs])."""

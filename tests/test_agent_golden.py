@@ -171,6 +171,88 @@ def test_agent_api_on_batched_env():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_whole_sac_loop_checkpoint_resume_is_exact(tmp_path, use_graph):
+    """the reference checkpoints network weights only (base_network.py:13-17).  Here the env
+    blob, the replay ring (rows, store counter, Philox sample counter), the Adam moments + step counter and the
+    CUDA generator state are saved too: save -> keep running == fresh objects -> load -> run, bit for bit
+    (observations, sampled batches, losses, weights)."""
+    cfg = S.load_config(base_settings__experiment=6, agent__batch_size=256)
+
+    def make():
+        env = S.BatchedBoatEnv(cfg, 2048, seed=3, precision="fp32", device=0, auto_reset=True)
+        mem = S.ReplayBuffer(30_000, (11,), 1, precision="fp32", device=0, seed=7, as_torch=True)   # wraps inside the run
+        agent = ContinuousAgent(cfg, str(tmp_path), (11,), env, device=0, seed=3, memory=mem, use_cuda_graph=use_graph)
+        return env, mem, agent
+
+    def run(env, agent, iters):
+        out = []
+        obs = env.obs
+        for _ in range(iters):
+            a = agent.choose_action(obs)
+            agent.step_and_remember(env, a.squeeze(-1))
+            losses = agent.learn()
+            out.append((env.obs.clone(), env.reward.clone(), torch.stack([x.detach().clone() for x in losses])))
+        return out
+
+    os.makedirs(tmp_path / "checkpoints", exist_ok=True)
+    env, mem, agent = make()
+    env.reset()
+    run(env, agent, 25)                       # the ring wraps at iteration 15
+    torch.save({"env": env.state_dict(), "agent": agent.state_dict()}, tmp_path / "full.pt")
+    assert agent.save_training_state() == str(tmp_path / "checkpoints" / "training_state.pt")
+    tail_a = run(env, agent, 12)
+    weights_a = [p.detach().clone() for net in agent.learner.networks() for p in net.parameters()]
+    cntr_a = mem.mem_cntr
+
+    env2, mem2, agent2 = make()               # what a fresh process does
+    ck = torch.load(tmp_path / "full.pt", weights_only=False)
+    env2.load_state_dict(ck["env"])
+    agent2.load_state_dict(ck["agent"])
+    assert mem2.mem_cntr == 25 * 2048 and agent2.updates == 25
+    tail_b = run(env2, agent2, 12)
+    for (o1, r1, l1), (o2, r2, l2) in zip(tail_a, tail_b):
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(l1, l2)
+    weights_b = [p.detach().clone() for net in agent2.learner.networks() for p in net.parameters()]
+    assert all(torch.equal(p, q) for p, q in zip(weights_a, weights_b)) and mem2.mem_cntr == cntr_a
+    idx = torch.arange(0, 30_000, 7, device="cuda")
+    assert all(torch.equal(x, y) for x, y in zip(mem.gather(idx), mem2.gather(idx)))
+    other = S.ReplayBuffer(4096, (11,), 1, precision="fp32", device=0, as_torch=True)
+    with pytest.raises(ValueError):
+        other.load_state_dict(ck["agent"]["memory"])
+    for x in (env, env2, mem, mem2, other):
+        x.close()
+
+
+@pytest.mark.gpu
+def test_load_models_refreshes_the_acting_copies(tmp_path):
+    """load_models() in evaluation-only use (learn() never called): the packed bf16 blob of the tcgen05 policy and
+    the acting copies of an OverlappedActorLearner follow the loaded weights."""
+    cfg = S.load_config(base_settings__experiment=6, agent__batch_size=256)
+    os.makedirs(tmp_path / "checkpoints", exist_ok=True)
+    env = S.BatchedBoatEnv(cfg, 4096, seed=3, precision="fp32", device=0, auto_reset=True)
+    mem = S.ReplayBuffer(30_000, (11,), 1, precision="fp32", device=0, as_torch=True)
+    agent = ContinuousAgent(cfg, str(tmp_path), (11,), env, device=0, seed=3, memory=mem, policy_precision="tcgen05")
+    obs = env.reset()
+    agent.save_models()
+    pipe = S.OverlappedActorLearner(agent, env)
+    pol = agent.tensor_core_policy()
+    eps = torch.randn(4096, 1, device="cuda")
+    ref_act = pol.act(obs, eps).clone()
+    with torch.no_grad():
+        for p in agent.actor.parameters():
+            p.add_(0.25)
+    pol.refresh()
+    assert not torch.equal(pol.act(obs, eps), ref_act)
+    agent.load_models()                                   # weights back; no learn() afterwards
+    assert torch.equal(pol.act(obs, eps), ref_act)
+    torch.cuda.synchronize()
+    for c in pipe.acting:
+        assert all(torch.equal(p, q) for p, q in zip(c.parameters(), agent.actor.parameters()))
+    env.close(); mem.close()
+
+
+@pytest.mark.gpu
 def test_overlapped_actor_learner():
     """Acting and learning on two streams: same env trajectory bookkeeping as the sequential loop (every
     step stores n transitions, one update per step once a batch exists), finite losses, and the acting

@@ -60,3 +60,25 @@ def test_reference_recorded_headers_match():
     from sac_agent_b200 import experiment as E
     assert open(os.path.join(base, "console.csv")).readline().strip().split(";") == E.CONSOLE_COLUMNS
     assert open(os.path.join(base, "terminations.csv")).readline().strip().split(";") == E.INFO_KEYS
+
+
+def test_saved_configs_carry_every_reference_key(tmp_path):
+    """A default run's tuned_configs.yaml must be readable by the reference's post-processing, which slices with
+    base_settings.avg_lookback (rendering/boat_env_render.py:31, postprocessing/replayer.py:52): every key of the
+    reference's configs/original_config.yaml is present with the shipped value, also for a partial config."""
+    import yaml
+    exp = S.Experiment(root=str(tmp_path), rng=random.Random(1))
+    tuned = exp.save_configs()                                     # config.DEFAULTS
+    assert isinstance(tuned.base_settings.avg_lookback, int) and tuned.base_settings.avg_lookback == 50
+    assert tuned.base_settings.n_games == 250 and tuned.base_settings.render_skip_size == 50
+    assert tuned.boat.n_max == 30 and tuned.agent.layer1_size == 256 and tuned.boat.a == 4.252
+    scores = list(range(100))
+    assert scores[-tuned.base_settings.avg_lookback:] == scores[50:]   # the slice replayer.py:52 takes
+    exp2 = S.Experiment(experiment_name="second", root=str(tmp_path), rng=random.Random(2))
+    partial = {"base_settings": {"experiment": 3, "dt": 0.25, "t_max": 2500, "test_mode": 0}, "wind": {"max_velocity": 0.4}}
+    t2 = exp2.save_configs(partial)
+    assert t2.base_settings.experiment == 3 and t2.base_settings.avg_lookback == 50 and t2.wind.max_velocity == 0.4
+    ref = "/root/reference/configs/original_config.yaml"
+    if os.path.isfile(ref):                                        # key-for-key equality with the reference's file
+        with open(ref) as f:
+            assert yaml.safe_load(f) == S.config.DEFAULTS

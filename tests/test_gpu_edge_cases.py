@@ -283,3 +283,34 @@ def test_whole_launch_step_is_deterministic(S):
             torch.cuda.synchronize()
             assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), (trial, t)
         a.close(); b.close()
+
+
+def test_fp32_exact_carriers_field_round_trip(S):
+    """fp32 mode: rudder (44-bit fixed point, 2^-42 rad) and s_x / s_y (int32 fixed point) are exchanged as plain
+    numbers by get_field / set_field / env_state_host; the step index shares its word with the rudder's low bits."""
+    import ctypes as C
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    env = S.BatchedBoatEnv(cfg, 70, seed=5, precision="fp32", device=0, auto_reset=False)
+    env.reset()
+    rud = torch.linspace(-1.2, 1.2, 70, device=env.device)
+    sx = torch.linspace(0.0, 3899.0, 70, device=env.device)
+    sy = torch.linspace(-799.0, 799.0, 70, device=env.device)
+    env.set_field("rudder_angle", rud); env.set_field("s_x", sx); env.set_field("s_y", sy)
+    env.set_field("index", torch.arange(70, dtype=torch.int32, device=env.device) * 100)
+    assert torch.allclose(env.get_field("rudder_angle"), rud, atol=1e-9, rtol=0)      # 2^-42 rad resolution, then fp32
+    assert torch.allclose(env.get_field("s_x"), sx, atol=2e-6, rtol=0) and torch.allclose(env.get_field("s_y"), sy, atol=5e-7, rtol=0)
+    assert torch.equal(env.get_field("index"), torch.arange(70, dtype=torch.int32, device=env.device) * 100)
+    env.set_field("rudder_angle", rud * 0.5)                                         # must not disturb the index bits
+    assert torch.equal(env.get_field("index"), torch.arange(70, dtype=torch.int32, device=env.device) * 100)
+    out = (C.c_double * 10)()
+    assert env._L.boatenv_env_state_host(env._h, 69, out) == 0
+    assert abs(out[3] - 0.6) < 1e-7 and abs(out[4] - 3899.0) < 2e-6 and abs(out[5] - 799.0) < 5e-7 and out[8] == 6900
+    # thresholds: rudder just below / above pi/3 (boat_env.py:102), s_x just below / at the goal line (:85)
+    import math
+    env.set_field("rudder_angle", torch.full((70,), math.pi / 3 - 0.05, device=env.device))
+    env.set_field("s_x", torch.full((70,), 100.0, device=env.device)); env.set_field("s_y", torch.zeros(70, device=env.device))
+    a = torch.zeros(70, device=env.device); a[1] = 0.4999; a[2] = 0.5001
+    _, _, done, info = env.step(a)
+    assert info["term"][:3].tolist() == [0, 0, 5] and done[:3].tolist() == [0, 0, 1]
+    env.close()

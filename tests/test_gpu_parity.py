@@ -115,9 +115,14 @@ def test_golden_rollouts_fp32(S, name):
 # ---------------------------------------------------------------------------------------
 # 2. the reference's recorded fixtures (ressources/settings_visualized): known answers
 # ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6])
-def test_recorded_fixture_replay(S, n):
+def test_recorded_fixture_replay(S, n, precision):
+    """The reference's six recorded episodes (test_mode 1: the boat runs straight to the goal line in 4959 / 4963
+    steps).  fp64: 1e-11; fp32 production mode: the same STEP COUNT and termination (s_x is carried in fixed point,
+    so 5000 accumulations do not move the goal crossing) and 1e-4 on the recorded quantities."""
     g = load_golden(f"fixture_exp{n}")
+    tol, rtol = (1e-11, 1e-11) if precision == "fp64" else (TOL32, 2e-4)
     fp = int(g["config"]["wind"]["fixed_points"])
     knots = np.zeros((1, 2, fp))
     if g["meta"]["kind_v"] == "curve":
@@ -126,7 +131,7 @@ def test_recorded_fixture_replay(S, n):
         knots[0, 1] = g["knots_a"]
     if g["meta"]["kind_a"] == "rect":  # exp 5: the first drawn curve is the rect source (wind.py:57)
         knots[0, 0] = g["knots_r"]
-    env = make_env(S, g["config"], 1, "fp64", np.array([int(g["s_y_start"])]), knots, auto_reset=False)
+    env = make_env(S, g["config"], 1, precision, np.array([int(g["s_y_start"])]), knots, auto_reset=False)
     env.reset()
     wv, wa = env.wind_table(0)
     assert np.abs(wv[g["wind_idx"]] - g["wind_v"]).max() < 5e-14
@@ -142,9 +147,9 @@ def test_recorded_fixture_replay(S, n):
             row = ref[want[steps]]
             for col, f, scale in ((0, "s_x", 3900.0), (1, "s_y", 800.0), (2, "v_x", 5.0), (3, "v_y", 2.0),
                                   (4, "s_r", 2 * np.pi)):
-                assert scaled_err(np_(env.get_field(f))[0], row[col], scale) <= 1e-11
+                assert scaled_err(np_(env.get_field(f))[0], row[col], scale) <= tol
             if steps > 0:
-                assert abs(float(rew[0]) + offset - row[6]) <= 1e-11
+                assert abs(float(rew[0]) + offset - row[6]) <= rtol
         obs, rew, d, info = env.step(zero)
         done = bool(d[0].item())
         ep_reward += float(rew[0])
@@ -152,7 +157,7 @@ def test_recorded_fixture_replay(S, n):
     assert steps == int(g["n_rows"])  # the terminal step is never written (main.py:79-81)
     assert int(info["term"][0]) == 1 and str(g["termination"]) == "reached_goal"
     if n == 6:
-        assert ep_reward == pytest.approx(871.2727580297085, abs=1e-8)
+        assert ep_reward == pytest.approx(871.2727580297085, abs=1e-8 if precision == "fp64" else 0.05)
     env.close()
 
 
@@ -217,15 +222,17 @@ def test_synchronised_piece_crossings_flood_the_setup_queue(S, O, precision):
     env.close()
 
 
-@pytest.mark.parametrize("precision", ["fp64", "fp32"])
-def test_auto_reset_matches_oracle(S, O, precision):
+@pytest.mark.parametrize("precision,seed", [("fp64", 3), ("fp32", 1), ("fp32", 2), ("fp32", 3), ("fp32", 4), ("fp32", 5)])
+def test_auto_reset_matches_oracle(S, O, precision, seed):
     """Uniform(-1,1) policy A1: episodes end by rudder_broken every ~360 steps; the kernel
     resets in place with the next episode's Philox draws.  Step counts, termination kinds
-    and statistics must equal the oracle's; terminal observations go to final_obs."""
+    and statistics must equal the oracle's; terminal observations go to final_obs.  No seed is special: the fp32
+    mode carries the rudder in 2^-42 rad fixed point, so the pi/3 and pi/4 thresholds (boat_env.py:102,107) fall
+    on the reference's step (round 1 passed only on seeds that happened not to cross within 1e-6)."""
     cfg = S.load_config(base_settings__experiment=6)
-    n, T, E = 512, 1500, 40
-    env = make_env(S, cfg, n, precision, seed=3, auto_reset=True)
-    s_y, knots = host_draws(env, E)
+    n, T, E = 2048, 1500, 40
+    env = make_env(S, cfg, n, precision, seed=seed, auto_reset=True)
+    s_y, knots = env.episode_draws_batch(np.arange(n), E)
     env.reset()
     import torch
     actions = np_(torch.stack([env.uniform_actions(t, 1.0).clone() for t in range(T)]))
@@ -276,9 +283,9 @@ def test_step_k_equals_k_single_steps(S):
             assert torch.allclose(rsum[ok], rb[ok], rtol=1e-5 if precision == "fp32" else 1e-12, atol=0)
             assert torch.all(db[ok] == 0) and torch.all(info["steps"][ok] == K)
             assert torch.all(db[~ok] == 1)
-            # resynchronise b's finished envs with a (a kept stepping them)
-            for f in ("v_x", "v_y", "v_r", "rudder_angle", "s_x", "s_y", "s_r", "episode_reward", "index"):
-                b.set_field(f, a.get_field(f))
+            # resynchronise b's finished envs with a (a kept stepping them): the state blob is an exact copy
+            # (set_field(get_field()) rounds the fp32 mode's fixed-point rudder / positions to fp32)
+            b.load_state_dict(a.state_dict())
         a.close(); b.close()
 
 
@@ -409,6 +416,65 @@ def test_step_host_equals_step(S, n, pinned):
         b.step_host(act_h, obs_h, rew_h, done_h)
         assert torch.equal(o.cpu(), obs_h) and torch.equal(r.cpu(), rew_h) and torch.equal(d.cpu(), done_h)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("n,precision", [(300_000, "fp32"), (1000, "fp32"), (70_000, "fp64")])
+def test_step_k_host_equals_step_k(S, n, precision):
+    """boatenv_step_k_host (actions [K][N] from host memory, one observation per env back) == boatenv_step_k on a
+    twin, bit for bit, incl. the deferred episode-end queue and the chunked copy / compute pipeline."""
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    K = 8
+    a = make_env(S, cfg, n, precision, seed=2, auto_reset=True)
+    b = make_env(S, cfg, n, precision, seed=2, auto_reset=True)
+    a.reset(); b.reset()
+    dt = a.dtype
+    act_h = torch.empty((K, n), dtype=dt).pin_memory()
+    obs_h = torch.empty((n, 11), dtype=dt).pin_memory()
+    rew_h = torch.empty(n, dtype=dt).pin_memory()
+    done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    term_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    steps_h = torch.empty(n, dtype=torch.int32).pin_memory()
+    for w in range(10):
+        acts = torch.stack([a.uniform_actions(w * K + k, 3.0).clone() for k in range(K)])
+        act_h.copy_(acts)
+        o, r, d, info = a.step_k(acts, K)
+        torch.cuda.synchronize()
+        b.step_k_host(act_h, K, obs_h, rew_h, done_h, term_h, steps_h)
+        assert torch.equal(o.cpu(), obs_h) and torch.equal(r.cpu(), rew_h) and torch.equal(d.cpu(), done_h)
+        assert torch.equal(info["term"].cpu(), term_h) and torch.equal(info["steps"].cpu(), steps_h)
+    assert int(done_h.sum()) > 0
+    ca, cb = a.counters(), b.counters()
+    assert ca["episodes"] == cb["episodes"] > 0
+    a.close(); b.close()
+
+
+def test_step_host_does_not_serialise_other_streams(S):
+    """boatenv_step_host_stream waits for an EVENT on the caller's stream, not for the device: a long kernel queued
+    on an unrelated stream is still running when step_host returns."""
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    n = 4096
+    env = make_env(S, cfg, n, "fp32", seed=2, auto_reset=True)
+    env.reset()
+    act_h = torch.zeros(n, dtype=torch.float32).pin_memory()
+    obs_h = torch.empty((n, 11), dtype=torch.float32).pin_memory()
+    rew_h = torch.empty(n, dtype=torch.float32).pin_memory()
+    done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    env.step_host(act_h, obs_h, rew_h, done_h)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    x = torch.randn(8192, 8192, device="cuda")
+    marker = torch.cuda.Event()
+    with torch.cuda.stream(side):
+        for _ in range(40):          # ~100 ms of matmuls on the side stream
+            x = (x @ x).clamp_(-1, 1)
+        marker.record()
+    env.step_host(act_h, obs_h, rew_h, done_h)
+    still_running = not marker.query()
+    torch.cuda.synchronize()
+    assert still_running, "step_host waited for an unrelated stream (device-wide synchronise?)"
+    env.close()
 
 
 def test_error_behaviour(S):
