@@ -346,18 +346,24 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    t = 0
-    for _ in range(PREROLL + args.warmup):              # untimed: pre-roll to the steady-state reset rate, then warm-up
-        one_step(t)
-        t += 1
-    reduce_stats()
-    episodes_before = float(stats[5].item())
+    # everything slow on the host (NVML initialisation, event creation) happens BEFORE the warm-up, so that the GPU
+    # goes from the last warm-up step into the timed region without idling (a ~100 ms idle gap lets the clocks drop
+    # and made a 20-step timed region read 2-3 % slower than a 1000-step one)
     kernel_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                      for _ in range(args.steps)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
-    barrier()
+    t = 0
+    for _ in range(PREROLL):                            # untimed pre-roll to the steady-state reset rate
+        one_step(t)
+        t += 1
+    reduce_stats()
+    episodes_before_warmup = float(stats[5].item())
     sampler.start()
+    for _ in range(args.warmup):                        # W untimed warm-up steps, straight into the timed region
+        one_step(t)
+        t += 1
+    barrier()
     launches0 = lib.boatenv_kernel_launches()
     n_allreduce[0] = 0
     start.record()
@@ -371,7 +377,9 @@ def run_ours(args) -> None:
     clocks = sampler.stop()
     allreduces_timed = n_allreduce[0]
     reduce_stats()
-    episodes_timed = float(stats[5].item()) - episodes_before   # all ranks (stats is all-reduced)
+    # episodes that ended in warm-up + timed steps, scaled to the timed steps (the rate is steady after the pre-roll;
+    # counting exactly would need a host read-back between warm-up and timed region, i.e. the idle gap avoided above)
+    episodes_timed = (float(stats[5].item()) - episodes_before_warmup) * args.steps / (args.steps + args.warmup)
     elapsed_ms = start.elapsed_time(end)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / max(1, args.steps)
     tmax = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)

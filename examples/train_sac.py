@@ -53,6 +53,9 @@ def main(argv=None):
                     help="population mode (main.py -p): every rank trains with its own tuned_configs.yaml draw")
     ap.add_argument("--policy-precision", default="fp32", choices=["fp32", "tf32", "bf16", "tcgen05"],
                     help="dense layers of choose_action on tensor-core inputs (acting only; the learner stays fp32)")
+    ap.add_argument("--pbt-every", type=int, default=0,
+                    help="population-based training (with torchrun, one member per GPU): every this many iterations the "
+                         "bottom quarter adopts the best member's weights + hyper-parameters and perturbs them")
     ap.add_argument("--overlap", action="store_true",
                     help="acting and learning on two streams (OverlappedActorLearner: the policy lags one update)")
     args = ap.parse_args(argv)
@@ -82,6 +85,8 @@ def main(argv=None):
     pipe = S.OverlappedActorLearner(agent, env, done_flag_mode=1) if args.overlap else None
     losses = None
     rows, best, prev = [], float("-inf"), {"episodes": 0.0, "return_sum": 0.0}
+    import random as _random
+    pbt_prev, pbt_log, pbt_rng = {"episodes": 0.0, "return_sum": 0.0}, [], _random.Random(1000 + args.seed + rank)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for it in range(1, args.warmup_iters + args.iters + 1):
         if it == args.warmup_iters + 1:
@@ -96,6 +101,19 @@ def main(argv=None):
             for _ in range(args.updates_per_iter):
                 out = agent.learn()
                 losses = out if out is not None else losses
+        if args.pbt_every and world > 1 and it % args.pbt_every == 0:
+            if pipe:
+                pipe.sync()
+            c = env.counters()
+            n = c["episodes"] - pbt_prev["episodes"]
+            score = (c["return_sum"] - pbt_prev["return_sum"]) / n if n else float("nan")
+            pbt_prev = c
+            hp, info = S.population.exploit_explore(agent.training_tensors(), agent.hyperparameters(), score, pbt_rng)
+            if info["adopted_from"] is not None:
+                agent.set_hyperparameters(**hp)
+                agent._weights_changed()
+            pbt_log.append({"iter": it, "score": score, "adopted_from": info["adopted_from"], "hp": hp,
+                            "ranking": info["ranking"]})
         if pipe and args.log_every and it % args.log_every == 0:
             pipe.sync()   # counters, losses and checkpoints below run on the default stream: order it after the pipeline
         if exp and args.log_every and it % args.log_every == 0:
@@ -132,6 +150,10 @@ def main(argv=None):
                "ms_per_iter": 1e3 * sec / args.iters, "episodes": stats["episodes"],
                "mean_return": stats["return_mean"], "reached_goal": stats["reached_goal"],
                "losses_v_pi_q": [float(x) for x in losses] if losses is not None else None}
+    if args.pbt_every:
+        summary["pbt_rounds"] = len(pbt_log)
+        summary["pbt_adoptions_rank0"] = [e for e in pbt_log if e["adopted_from"] is not None]
+        summary["hyperparameters_rank0"] = agent.hyperparameters()
     if exp:
         c = env.counters()
         exp.write_console(rows)

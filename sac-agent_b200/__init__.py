@@ -15,6 +15,7 @@ from .toy_envs import ToyCar, ToyParachute  # noqa: F401
 from .csv_export import BatchedRecorder  # noqa: F401
 from .sharding import all_reduce_counters, make_sharded_env, shard_range  # noqa: F401
 from .experiment import Experiment, HPTuner, get_experiment_config, info_from_counters  # noqa: F401
+from . import population  # noqa: F401
 
 __all__ = ["AttrDict", "load_config", "params_from_config", "BoatEnvError", "lib", "library_path",
            "BatchedBoatEnv", "BoatEnv", "Box", "TERM_NAMES", "ReplayBuffer", "ToyCar", "ToyParachute",

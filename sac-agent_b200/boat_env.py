@@ -23,19 +23,32 @@ FIELDS = {"v_x": 0, "v_y": 1, "v_r": 2, "rudder_angle": 3, "s_x": 4, "s_y": 5, "
 COUNTER_NAMES = ("reached_goal", "out_of_bounds", "out_of_fuel", "timeout", "rudder_broken",
                  "episodes", "return_sum", "return_sumsq")
 
-try:  # the reference's spaces come from gym 0.26 (boat_env.py:2)
-    from gym.spaces import Box  # type: ignore
-except Exception:  # gym is not a dependency of this package
-    class Box:  # minimal stand-in with the attributes BaseAgent reads (base_agent.py:7-19)
-        def __init__(self, low, high, shape=None, dtype=np.float32):
-            low = np.asarray(low, dtype=dtype)
-            high = np.asarray(high, dtype=dtype)
-            if low.ndim == 0:  # scalar bounds and no shape: gym 0.26 infers (1,)
-                low, high = low.reshape(1), high.reshape(1)
-            self.low, self.high, self.shape, self.dtype = low, high, low.shape, np.dtype(dtype)
+class _FallbackBox:
+    """Minimal stand-in for gym.spaces.Box with the attributes BaseAgent reads (base_agent.py:7-19)."""
 
-        def sample(self):
-            return np.random.uniform(self.low, self.high).astype(self.dtype)
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        low = np.asarray(low, dtype=dtype)
+        high = np.asarray(high, dtype=dtype)
+        if low.ndim == 0:  # scalar bounds and no shape: gym 0.26 infers (1,)
+            low, high = low.reshape(1), high.reshape(1)
+        self.low, self.high, self.shape, self.dtype = low, high, low.shape, np.dtype(dtype)
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+
+def _box_class():
+    """The reference's spaces come from gym 0.26 (boat_env.py:2) and BaseAgent tests ``isinstance(action_space,
+    gym.spaces.Box)`` (base_agent.py:9): whenever a ``gym`` is importable when an env is built, its Box is used, so
+    that check holds for the drop-in; gym itself is not a dependency of this package."""
+    try:
+        from gym.spaces import Box as GymBox  # type: ignore
+        return GymBox
+    except Exception:
+        return _FallbackBox
+
+
+Box = _box_class()
 
 
 def _torch():
@@ -74,9 +87,10 @@ class BatchedBoatEnv:
         self.done = torch.empty(n, dtype=torch.uint8, device=self.device)
         self.term = torch.empty(n, dtype=torch.uint8, device=self.device)
         self.final_obs = torch.zeros((n, 11), dtype=self.dtype, device=self.device)
-        self.observation_space = Box(low=np.array([0] * 10 + [1], dtype=np.float32),
+        box = _box_class()   # resolved now, not at import time: a gym imported in between is honoured
+        self.observation_space = box(low=np.array([0] * 10 + [1], dtype=np.float32),
                                      high=np.array([1] * 10 + [0], dtype=np.float32), dtype=np.float32)
-        self.action_space = Box(low=-1, high=1, dtype=np.float32)  # boat_env.py:37-41
+        self.action_space = box(low=-1, high=1, dtype=np.float32)  # boat_env.py:37-41
 
     # -- life cycle ---------------------------------------------------------------
     def close(self):

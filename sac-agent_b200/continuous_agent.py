@@ -366,6 +366,35 @@ class ContinuousAgent:
             net.load_checkpoint()
         self._weights_changed()
 
+    # -- population-based training hooks (population.py) -------------------------------------------------------
+    def hyperparameters(self):
+        """The four keys the reference's tuner draws (utils/hyperparameter_tuner.py:9-52)."""
+        o = self.learner.optimizer
+        n_actor = len(self.learner._actor_params)
+        return {"alpha": float(o._slots[0].lr), "beta": float(o._slots[n_actor].lr), "gamma": float(self.learner.gamma),
+                "tau": float(self.learner.tau)}
+
+    def set_hyperparameters(self, alpha=None, beta=None, gamma=None, tau=None):
+        """New learning rates / discount / target smoothing for the following updates.  The captured update graph
+        holds the old values as kernel arguments, so it is dropped and re-captured by the next learn()."""
+        L, o = self.learner, self.learner.optimizer
+        n_actor = len(L._actor_params)
+        for k in range(len(o.params)):
+            if k < n_actor and alpha is not None:
+                o._slots[k].lr = float(alpha)
+            if k >= n_actor and beta is not None:
+                o._slots[k].lr = float(beta)
+        if gamma is not None:
+            L.gamma = self.gamma = float(gamma)
+        if tau is not None:
+            L.tau = o.tau = self.tau = float(tau)
+        self._graph = None
+
+    def training_tensors(self):
+        """Weights of the five networks + Adam moments and step counter: what a population member hands over."""
+        L = self.learner
+        return [p.data for net in L.networks() for p in net.parameters()] + L.optimizer.state_tensors()
+
     def _weights_changed(self):
         if self._tc_policy is not None:
             self._tc_policy.refresh()

@@ -237,8 +237,10 @@ static int derive_config(const boatenv_params *p, DevCfg &c) {
         f.sy_inv = (float)(1.0 / (double)(1LL << f.sy_shift));
         f.sx_goal = (int)std::ceil(p->goal_line * (double)(1LL << f.sx_shift));
         f.sy_oob = (int)std::floor((p->track_width + p->oob_offset) * (double)(1LL << f.sy_shift));
-        f.rud_pi3 = (long long)std::floor((PI / 3.0) * 4398046511104.0);
-        f.rud_pi4 = (long long)std::floor((PI / 4.0) * 4398046511104.0);
+        f.rud_pi3 = std::floor((PI / 3.0) * 4398046511104.0);
+        f.rud_pi4 = std::floor((PI / 4.0) * 4398046511104.0);
+        f.sx_obs = (float)(1.0 / (double)(1LL << f.sx_shift) / p->goal_line);
+        f.sy_obs = (float)(1.0 / (double)(1LL << f.sy_shift) / (2.0 * p->track_width));
     }
     return BOATENV_OK;
 }

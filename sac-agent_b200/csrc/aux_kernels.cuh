@@ -4,85 +4,96 @@
 
 namespace boatenv {
 
-// BoatEnv.reset()  boat_env.py:120-126 for the masked envs: a new Boat (:144-201) and a
-// new Wind (wind.py:12-18).  Each warp serves its 32 envs one at a time with the
-// cooperative wind_setup_warp().
-template <typename T>
-__global__ void __launch_bounds__(kTile) boat_reset_kernel(const __grid_constant__ DevCfg c, const uint8_t *mask,
-                                                          T *obs_out) {
-    __shared__ double scratch_s[kWarpsPerCta][kScratchDoubles];
+// BoatEnv.reset()  boat_env.py:120-126 for the masked envs: a new Boat (:144-201) and a new Wind (wind.py:12-18).
+// Two instantiations share the body.  LANE = true sets the wind up one env per LANE (no cooperation; 128 registers):
+// it serves the warps with many envs to reset -- all of them in a full reset.  LANE = false serves the warps with only
+// a few (a sparse mask) one env at a time with the warp-cooperative mapping, which finishes a single env ~5x sooner
+// and runs at four times the occupancy.  A masked reset launches both; each skips the other's warps.  The two
+// mappings give bit-identical coefficients (wind_setup.cuh).
+constexpr int kResetLaneParallelFrom = 5;   // envs per warp from which the lane-parallel mapping is the faster one
+template <typename T, bool LANE>
+__global__ void __launch_bounds__(kTile, LANE ? 2 : 4) boat_reset_kernel(const __grid_constant__ DevCfg c,
+                                                                    const uint8_t *mask, T *obs_out) {
+    __shared__ double scratch_s[LANE ? 1 : kWarpsPerCta][LANE ? 1 : kScratchDoubles];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
-    const bool active = i < c.n_envs;
-    const bool want = active && (mask == nullptr || mask[i] != 0);
-    uint32_t episode = 0;
-    if (want) episode = *episode_ptr(c, i) + 1u;
-    // experiments 1-3 draw no wind curves: nothing is warp-cooperative, every lane resets its own env at once
-    unsigned todo = c.ncurves > 0 ? __ballot_sync(FULL, want) : (want ? 1u : 0u);
-    while (todo) {
-        const int src = c.ncurves > 0 ? __ffs(todo) - 1 : lane;
-        todo &= todo - 1;
-        if (c.ncurves > 0) {
-            const long long e_env = __shfl_sync(FULL, i, src);
-            const uint32_t e_epi = __shfl_sync(FULL, episode, src);
-            wind_setup_warp(c, e_env, e_epi, 0, scratch_s[warp]);
-        }
-        const uint32_t e_epi = episode;   // the lane that owns env `src` (the only one that enters below)
-        if (lane == src) {
-            T d[D_COUNT], wa[4], wb[4], obs[kObsDim];
-            const int sy0 = episode_start_y(c, i, e_epi);  // boat_env.py:166-167
-            Fx<T> fx;
-            fx.start(c, d, sy0);
-            fx.pack(d);
+    const bool want = i < c.n_envs && (mask == nullptr || mask[i] != 0);
+    double w8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    unsigned todo = __ballot_sync(FULL, want);
+    // which instantiation owns this warp: experiments without curves need no setup (LANE owns everything)
+    const bool lane_warp = c.ncurves == 0 || mask == nullptr || __popc(todo) >= kResetLaneParallelFrom;
+    if (lane_warp != LANE) return;
+    const uint32_t e_epi = want ? *episode_ptr(c, i) + 1u : 0u;
+    if (c.ncurves > 0) {
+        if (LANE) {
+            if (want) wind_setup_lane_any(c, i, e_epi, 0, w8);
+        } else {
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                wind_setup_warp(c, __shfl_sync(FULL, i, src), __shfl_sync(FULL, e_epi, src), 0, scratch_s[LANE ? 0 : warp]);
+                if (lane == src) {
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                wa[m] = c.ncurves > 0 ? (T)scratch_s[warp][m] : (T)0;
-                wb[m] = c.ncurves > 0 ? (T)scratch_s[warp][4 + m] : (T)0;
-            }
-            store_vecs<T, D_COUNT>(block_section(c, i, 0), lane, d);
-            *index_ptr(c, i) = fx.index_word(0);
-            *episode_ptr(c, i) = e_epi;
-            if (c.ncurves >= 1) store_vecs<T, 4>(block_section(c, i, c.off_wa), lane, wa);
-            if (c.ncurves >= 2) store_vecs<T, 4>(block_section(c, i, c.off_wb), lane, wb);
-            if (obs_out) {
-                stage_reset_obs<T>(c, obs, (T)sy0);
-#pragma unroll
-                for (int q = 0; q < kObsDim; ++q) obs_out[i * kObsDim + q] = obs[q];
+                    for (int m = 0; m < 8; ++m) w8[m] = scratch_s[LANE ? 0 : warp][m];
+                }
+                __syncwarp();  // scratch is reused by the next env of this warp
             }
         }
-        if (c.ncurves > 0) __syncwarp();  // scratch is reused by the next env of this warp
+    }
+    if (!want) return;
+    T d[D_COUNT], wa[4], wb[4], obs[kObsDim];
+    const int sy0 = episode_start_y(c, i, e_epi);  // boat_env.py:166-167
+    Fx<T> fx;
+    fx.start(c, d, sy0);
+    fx.pack(d);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        wa[m] = (T)w8[m];
+        wb[m] = (T)w8[4 + m];
+    }
+    store_vecs<T, D_COUNT>(block_section(c, i, 0), lane, d);
+    *index_ptr(c, i) = fx.index_word(0);
+    *episode_ptr(c, i) = e_epi;
+    if (c.ncurves >= 1) store_vecs<T, 4>(block_section(c, i, c.off_wa), lane, wa);
+    if (c.ncurves >= 2) store_vecs<T, 4>(block_section(c, i, c.off_wb), lane, wb);
+    if (obs_out) {
+        stage_reset_obs<T>(c, obs, (T)sy0);
+#pragma unroll
+        for (int q = 0; q < kObsDim; ++q) obs_out[i * kObsDim + q] = obs[q];
     }
 }
 
 #ifndef BOAT_SETUPQ_MINBLOCKS
-#define BOAT_SETUPQ_MINBLOCKS 4
+#define BOAT_SETUPQ_MINBLOCKS 2
 #endif
-// Follow-up of a K > 1 step launch: the episode-end queue (one region per step CTA) is drained at full
-// occupancy -- one warp-cooperative wind setup per entry, the new episode's first-piece coefficients go
-// straight into the env's state block.  Warps are dealt to regions round-robin.
+// Follow-up of a K > 1 step launch: the episode-end queue (one region per step CTA) is drained one entry per
+// THREAD (lane-parallel wind setup); the new episode's first-piece coefficients go straight into the env's state
+// block.  Warps are dealt to regions round-robin; warp j of a region takes entries 32 j .. 32 j + 31, then
+// strides by 32 * warps_per_region.
 template <typename T>
 __global__ void __launch_bounds__(kTile, BOAT_SETUPQ_MINBLOCKS) boat_setup_queue_kernel(const __grid_constant__ DevCfg c,
                                                                    const uint2 *__restrict__ entries,
                                                                    const unsigned *__restrict__ counts, int n_regions,
                                                                    int cap, int warps_per_region) {
-    __shared__ double scratch_s[kWarpsPerCta][kScratchDoubles];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = (int)blockIdx.x * kWarpsPerCta + warp;
     const int region = w % n_regions, j0 = w / n_regions;
     if (j0 >= warps_per_region) return;
     const unsigned cnt = counts[region];
-    double *scr = scratch_s[warp];
-    for (unsigned e = (unsigned)j0; e < cnt; e += (unsigned)warps_per_region) {
-        const uint2 en = __ldg(entries + (size_t)region * cap + e);  // warp-uniform
-        wind_setup_warp(c, (long long)en.x, en.y, 0, scr);
-        if (lane < c.ncurves) {  // lane 0: first curve, lane 1: second curve
-            T w4[4];
+    for (unsigned e = (unsigned)j0 * 32u + (unsigned)lane; e < cnt; e += 32u * (unsigned)warps_per_region) {
+        const uint2 en = __ldg(entries + (size_t)region * cap + e);
+        double w8[8];
+        wind_setup_lane_any(c, (long long)en.x, en.y, 0, w8);
+        T w4[4];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) w4[m] = (T)scr[lane * 4 + m];
-            store_vecs<T, 4>(block_section(c, en.x, lane ? c.off_wb : c.off_wa), (int)(en.x & 31u), w4);
+        for (int m = 0; m < 4; ++m) w4[m] = (T)w8[m];
+        store_vecs<T, 4>(block_section(c, en.x, c.off_wa), (int)(en.x & 31u), w4);
+        if (c.ncurves >= 2) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) w4[m] = (T)w8[4 + m];
+            store_vecs<T, 4>(block_section(c, en.x, c.off_wb), (int)(en.x & 31u), w4);
         }
-        __syncwarp();
     }
 }
 

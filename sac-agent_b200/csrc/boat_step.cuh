@@ -147,14 +147,21 @@ __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], Fx
     // the rudder in 2^-42 rad units (boat_env.py:72-73 is a sum of action / 10 terms), s_x and s_y in fixed point.
     const FastConsts &f = c.f;
     const bool first = (index == 0);
+    // The fp32 VIEW of the new angle (what the dynamics and the observation use) is one FFMA behind the action:
+    // previous exact angle rounded to fp32, plus action / 10.  The EXACT update runs beside it on the fp64 pipe
+    // and only feeds the threshold tests at the end of the sub-step, so it is off the critical path
+    // action -> sin(rudder) -> a_y, a_r -> v -> s_r -> sincos -> positions.
+    float rudder = fx.rudder_view();
     if (c.test_mode == 0) {  // rudder += action / 10 (boat_env.py:72-73); |action| is nominally <= 1 and not clipped
+        // any |action| >= 21 breaks the rudder from any unbroken state, so clamping at 64 changes no outcome; the
+        // increment is rounded to a whole number of 2^-42 rad with the 1.5 * 2^52 trick (exact for |x| < 2^51)
         const float a_c = fminf(fmaxf(action, -64.0f), 64.0f);
-        fx.rud += __double2ll_rn((double)a_c * (4398046511104.0 / 10.0));
+        rudder = fmaf(a_c, f.tenth, rudder);
+        const double t = fma((double)a_c, 4398046511104.0 / 10.0, 6755399441055744.0);
+        fx.rud += t - 6755399441055744.0;
     }
-    const long long rud_abs = fx.rud < 0 ? -fx.rud : fx.rud;
+    const double rud_abs = fabs(fx.rud);
     const bool rud_broken = rud_abs > f.rud_pi3, rud_penalty = rud_abs > f.rud_pi4;
-    if (rud_abs > kRudLimit) fx.rud = fx.rud < 0 ? -kRudLimit : kRudLimit;  // saturate (only a boat already broken gets here)
-    const float rudder = fx.rudder_view();
     float v_x = d[D_VX], v_y = d[D_VY], v_r = d[D_VR];
 
     float F_Wx = 0.0f, F_Wy = 0.0f;
@@ -187,10 +194,9 @@ __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], Fx
     const float s_r = fmaf(v_r, f.dt, d[D_SR]);
     float sr, cr;
     fast_sincosf(s_r, sr, cr);
-    fx.sx = add_sat_s32(fx.sx, __float2int_rn(fmaf(v_x, cr, -v_y * sr) * f.sx_k));
-    fx.sy = add_sat_s32(fx.sy, __float2int_rn(fmaf(v_y, cr, v_x * sr) * f.sy_k));
-    const float s_x = (float)fx.sx * f.sx_inv;
-    const float s_y = (float)fx.sy * f.sy_inv;
+    fx.sx = add_sat_s32(fx.sx, fixed_increment(fmaf(v_x, cr, -v_y * sr), f.sx_k));
+    fx.sy = add_sat_s32(fx.sy, fixed_increment(fmaf(v_y, cr, v_x * sr), f.sy_k));
+    const float s_y = (float)fx.sy * f.sy_inv;   // the float view of s_x is only needed for the observation (stage_obs)
     const float ay = fabsf(s_y);
     float r = -__fdividef(ay * f.rew_inv_W, 1.0f + __expf(f.rew_k * (ay - f.rew_y0)));
     // termination cascade boat_env.py:84-105, lowest priority first (later selects override);
@@ -209,7 +215,7 @@ __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], Fx
 
     acc[0] = a_x; acc[1] = a_y; acc[2] = a_r;
     d[D_VX] = v_x; d[D_VY] = v_y; d[D_VR] = v_r; d[D_RUDDER] = rudder;
-    d[D_SX] = s_x; d[D_SY] = s_y; d[D_SR] = s_r; d[D_RET] += r;
+    d[D_SY] = s_y; d[D_SR] = s_r; d[D_RET] += r;
 }
 
 // A NaN bit pattern that no arithmetic instruction produces (their NaNs are canonical): see the stage-refill vote.
@@ -218,7 +224,7 @@ __device__ __forceinline__ bool is_poison(double v) { return __double_as_longlon
 
 // return_state  boat_env.py:308-326: the 11 normalised observations of an env, written to
 // its row of the warp's shared-memory staging tile.  `index` = Boat.index after the step.
-__device__ __forceinline__ void stage_obs(const DevCfg &c, double *row, const double (&d)[D_COUNT],
+__device__ __forceinline__ void stage_obs(const DevCfg &c, double *row, const double (&d)[D_COUNT], const Fx<double> &,
                                           const double (&acc)[3], int index) {
     const boatenv_params &p = c.p;
     const double PI = 3.14159265358979323846;
@@ -234,10 +240,10 @@ __device__ __forceinline__ void stage_obs(const DevCfg &c, double *row, const do
     row[9] = (d[D_RUDDER] - (-PI / 3.0)) / (PI / 3.0 - (-PI / 3.0));
     row[10] = (p.fuel - (double)index) / p.fuel;
 }
-__device__ __forceinline__ void stage_obs(const DevCfg &c, float *row, const float (&d)[D_COUNT],
+__device__ __forceinline__ void stage_obs(const DevCfg &c, float *row, const float (&d)[D_COUNT], const Fx<float> &fx,
                                           const float (&acc)[3], int index) {
     const FastConsts &f = c.f;
-    row[0] = d[D_SX] * f.inv_goal;
+    row[0] = (float)fx.sx * f.sx_obs;
     row[1] = d[D_VX] * f.inv_5;
     row[2] = acc[0] * f.inv_ax;
     row[3] = (d[D_SY] + f.W) * f.inv_2W;
@@ -687,7 +693,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                 rsum += rew;
                 ++nsteps;
                 index += 1;
-                if (code != BOATENV_TERM_NONE || k == ksteps - 1) stage_obs(c, row, d, acc, index);
+                if (code != BOATENV_TERM_NONE || k == ksteps - 1) stage_obs(c, row, d, fx, acc, index);
                 if (code != BOATENV_TERM_NONE) {
                     alive = false;
                     need_setup = true;  // statistics, and the reset if AUTO_RESET

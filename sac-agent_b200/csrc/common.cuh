@@ -62,7 +62,8 @@ struct FastConsts {
     int sx_shift, sy_shift;
     int sx_goal;                        // s_x >= goal_line        <=> sx >= sx_goal   (boat_env.py:85)
     int sy_oob;                         // abs(s_y) > W + offset   <=> |sy| > sy_oob   (boat_env.py:90)
-    long long rud_pi3, rud_pi4;         // abs(rudder) > pi/3, pi/4 <=> |rud| > rud_pi3, rud_pi4 (boat_env.py:102,107)
+    double rud_pi3, rud_pi4;            // abs(rudder) > pi/3, pi/4 <=> |rud| > rud_pi3, rud_pi4 (boat_env.py:102,107)
+    float sx_obs, sy_obs;               // 2^-sx_shift / goal_line, 2^-sy_shift / (2 W): fixed point -> normalised observation
 };
 
 struct DevCfg {
@@ -233,34 +234,43 @@ template <> struct Fx<double> {
     }
 };
 template <> struct Fx<float> {
-    long long rud;
+    // rudder angle in units of 2^-42 rad, held as an INTEGER-VALUED double while a launch runs (sums of integers
+    // below 2^53 are exact, and the fp64 pipe does them in 1 instruction where int64 needs 2-4); stored as 44 bits
+    double rud;
     int sx, sy;
     __device__ __forceinline__ void load(const DevCfg &, const float (&d)[D_COUNT], uint32_t ixw, int &index) {
         index = (int)(ixw & kIndexMask);
-        rud = (long long)(((unsigned long long)(long long)__float_as_int(d[D_RUDDER]) << kRudLoBits) |
-                          (unsigned long long)(ixw >> kIndexBits));
+        rud = fma((double)__float_as_int(d[D_RUDDER]), (double)(1 << kRudLoBits), (double)(ixw >> kIndexBits));
         sx = __float_as_int(d[D_SX]);
         sy = __float_as_int(d[D_SY]);
     }
+    __device__ __forceinline__ long long rud_bits() const {   // saturated to the 44 stored bits
+        return __double2ll_rn(fmin(fmax(rud, -(double)kRudLimit), (double)kRudLimit));
+    }
     // the bit patterns that go to HBM (d keeps its float views; call on a copy or right before the store)
     __device__ __forceinline__ void pack(float (&d)[D_COUNT]) const {
-        d[D_RUDDER] = __int_as_float((int)(rud >> kRudLoBits));
+        d[D_RUDDER] = __int_as_float((int)(rud_bits() >> kRudLoBits));
         d[D_SX] = __int_as_float(sx);
         d[D_SY] = __int_as_float(sy);
     }
     __device__ __forceinline__ uint32_t index_word(int index) const {
-        return (uint32_t)index | (((uint32_t)rud & ((1u << kRudLoBits) - 1u)) << kIndexBits);
+        return (uint32_t)index | (((uint32_t)rud_bits() & ((1u << kRudLoBits) - 1u)) << kIndexBits);
     }
-    __device__ __forceinline__ float rudder_view() const { return (float)(int)(rud >> kRudLoBits) * 9.31322574615478515625e-10f; }  // 2^-30
+    __device__ __forceinline__ float rudder_view() const { return (float)rud * 2.27373675443232059478759765625e-13f; }  // 2^-42
     __device__ __forceinline__ void start(const DevCfg &c, float (&d)[D_COUNT], int s_y0) {
 #pragma unroll
         for (int q = 0; q < D_COUNT; ++q) d[q] = 0.0f;
         d[D_SY] = (float)s_y0;
-        rud = 0;
+        rud = 0.0;
         sx = 0;
         sy = s_y0 * (1 << c.f.sy_shift);   // |s_y0| <= 0.8 W: no overflow (the shift leaves room for W + offset)
     }
 };
+
+// round-to-nearest integer of x * k for |x * k| < 2^22 without the conversion pipe (one FFMA + one IADD)
+__device__ __forceinline__ int fixed_increment(float x, float k) {
+    return __float_as_int(fmaf(x, k, 12582912.0f)) - 0x4B400000;
+}
 
 __device__ __forceinline__ void unpack(const float4 &v, float *o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 __device__ __forceinline__ void unpack(const double2 &v, double *o) { o[0] = v.x; o[1] = v.y; }

@@ -110,8 +110,12 @@ cudaError_t FN(launch_step_)(const DevCfg &c, const StepArgs &a, cudaStream_t st
 }
 
 cudaError_t FN(launch_reset_)(const DevCfg &c, const uint8_t *mask, void *obs_out, cudaStream_t st) {
-    boat_reset_kernel<REAL><<<grid_for(c.n_envs, kTile), kTile, 0, st>>>(c, mask, reinterpret_cast<REAL *>(obs_out));
+    boat_reset_kernel<REAL, true><<<grid_for(c.n_envs, kTile), kTile, 0, st>>>(c, mask, reinterpret_cast<REAL *>(obs_out));
     count_launch();
+    if (mask != nullptr && c.ncurves > 0) {   // warps with only a few envs to reset: the cooperative instantiation
+        boat_reset_kernel<REAL, false><<<grid_for(c.n_envs, kTile), kTile, 0, st>>>(c, mask, reinterpret_cast<REAL *>(obs_out));
+        count_launch();
+    }
     return cudaGetLastError();
 }
 

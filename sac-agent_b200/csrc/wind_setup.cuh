@@ -37,6 +37,94 @@ __device__ __forceinline__ void piece_of(const DevCfg &c, int index, int &j, int
     r = (int)(num - q * (uint32_t)c.Lm1);
 }
 
+// ---------------------------------------------------------------------------------
+// The arithmetic of one episode setup, shared by the two work mappings below (warp-cooperative: one env per
+// warp, used inside the step kernels where requests are sparse; lane-parallel: one env per lane, used by the reset
+// kernel and the episode-end queue kernel where they are dense).  Both mappings call exactly these functions with
+// the same operands, so their results are bit-identical.
+// ---------------------------------------------------------------------------------
+
+// coefficient m of piece j in the local coordinate s: c_m = sum_k basis[(j*4+m)*fp + k] * u_k  (two accumulators)
+__device__ __forceinline__ double coef_dot(const double *__restrict__ brow, const double *u, int fp) {
+    double acc0 = 0.0, acc1 = 0.0;
+    if (fp == 8) {  // the reference's default (original_config.yaml:63): fully unrolled
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            acc0 = fma(__ldg(brow + k), u[k], acc0);
+            acc1 = fma(__ldg(brow + k + 1), u[k + 1], acc1);
+        }
+    } else {
+        int k = 0;
+        for (; k + 1 < fp; k += 2) {
+            acc0 = fma(__ldg(brow + k), u[k], acc0);
+            acc1 = fma(__ldg(brow + k + 1), u[k + 1], acc1);
+        }
+        if (k < fp) acc0 = fma(__ldg(brow + k), u[k], acc0);
+    }
+    return acc0 + acc1;
+}
+
+// Extremal SAMPLES of spline piece `sub` with local coefficients k0..k3 (np.min / np.max of wind.py:87-89 restricted
+// to the samples piece_of() assigns to this piece): folded into mn / mx.
+// The discrete extremes of the curve sit at the first / last sample of a piece or next to a root of the
+// derivative.  Only the samples of THIS piece are looked at (evaluated with the same piece and local coordinate
+// the step kernel will use): a neighbour on the far side of a piece boundary is that piece's own first / last
+// sample.  Roots are LOCATED in fp32 -- a 4-sample window absorbs the location error -- candidates are EVALUATED
+// in fp64.
+__device__ __forceinline__ void piece_extremes(const DevCfg &c, int sub, double k0, double k1, double k2, double k3,
+                                               double &mn, double &mx) {
+    const int np = c.npieces;
+    const int first = __ldg(c.piece_bounds + 2 * sub), last = __ldg(c.piece_bounds + 2 * sub + 1);
+    const int r_base = sub * c.Lm1;
+    const bool has_samples = first <= last;  // a table shorter than the spline can leave a piece without samples
+    auto consider = [&](int index) {
+        if (!has_samples) return;
+        index = max(first, min(index, last));
+        const double sl = (double)(index * np - r_base) * c.inv_Lm1;
+        const double v = fma(fma(fma(k3, sl, k2), sl, k1), sl, k0);
+        mn = (v < mn) ? v : mn;  // no NaNs here: plain compares instead of fmin / fmax
+        mx = (v > mx) ? v : mx;
+    };
+    consider(first);
+    consider(last);
+    const float A = 3.0f * (float)k3, B = 2.0f * (float)k2, C0 = (float)k1;
+    const float nanf_ = __int_as_float(0x7fc00000);
+    float s1 = nanf_, s2 = nanf_;
+    if (fabsf(A) > 1e-6f * (fabsf(B) + fabsf(C0))) {
+        const float disc = fmaf(B, B, -4.0f * A * C0);
+        if (disc >= 0.0f) {
+            const float q = -0.5f * (B + copysignf(sqrtf(disc), B));
+            s1 = __fdividef(q, A);
+            if (q != 0.0f) s2 = __fdividef(C0, q);
+        }
+    } else if (B != 0.0f) {
+        s1 = __fdividef(-C0, B);
+    }
+    const float per_piece = c.per_piece, margin = 3.0f * c.inv_per_piece;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        const float sr = which ? s2 : s1;
+        if (sr > -margin && sr < 1.0f + margin) {
+            const int f = (int)floorf(((float)sub + sr) * per_piece);
+            consider(f - 1);
+            consider(f);
+            consider(f + 1);
+            consider(f + 2);
+        }
+    }
+}
+
+// Renormalisation (wind.py:87-89: iff a sample leaves [0,1]) and the experiment's scale folded into coefficient m of
+// curve `curve`: exp 4 / 6 velocity = curve * max_velocity (wind.py:49,62); exp 5: the rect threshold acts on the
+// curve itself; second curve of exp 6: curve * pi * 2 (wind.py:63).
+__device__ __forceinline__ double fold_coef(const DevCfg &c, int curve, int m, double cfm, double lo, double hi) {
+    double off = 0.0, inv = 1.0;
+    if (lo < 0.0 || hi > 1.0) { off = lo; inv = 1.0 / (hi - lo); }
+    const double scale = curve ? 3.14159265358979323846 * 2.0
+                               : ((c.wind_kind == WIND_ANGLE_RECT) ? 1.0 : c.p.max_velocity);
+    return ((m == 0) ? (cfm - off) : cfm) * inv * scale;
+}
+
 // Called by all 32 lanes with warp-uniform arguments.  On return scratch[m] (m = 0..3) holds
 // the folded coefficients of the first drawn curve's piece containing sample `index_next`
 // (exp 4/6: velocity, exp 5: the rect source) and scratch[4 + m] those of the second drawn
@@ -63,77 +151,17 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
         if (t < total) {
             const int curve = (t >= np * 4) ? 1 : 0;
             const int rem = t - curve * np * 4;              // piece * 4 + m
-            const double *brow = c.basis + (size_t)rem * fp;
-            const double *u = kn + curve * kMaxKnots;
-            double acc0 = 0.0, acc1 = 0.0;
-            if (fp == 8) {  // the reference's default (original_config.yaml:63): fully unrolled
-#pragma unroll
-                for (int k = 0; k < 8; k += 2) {
-                    acc0 = fma(__ldg(brow + k), u[k], acc0);
-                    acc1 = fma(__ldg(brow + k + 1), u[k + 1], acc1);
-                }
-            } else {
-                int k = 0;
-                for (; k + 1 < fp; k += 2) {
-                    acc0 = fma(__ldg(brow + k), u[k], acc0);
-                    acc1 = fma(__ldg(brow + k + 1), u[k + 1], acc1);
-                }
-                if (k < fp) acc0 = fma(__ldg(brow + k), u[k], acc0);
-            }
-            coef[t] = acc0 + acc1;
+            coef[t] = coef_dot(c.basis + (size_t)rem * fp, kn + curve * kMaxKnots, fp);
         }
     }
     __syncwarp();
 
-    // --- extremal samples of every piece (np.min / np.max of wind.py:87-89) -----------------
-    // The discrete extremes of the curve sit at the first / last sample of a piece or next to a root of
-    // the derivative.  Every lane looks only at the samples of ITS piece (evaluated from registers with
-    // the same piece and local coordinate the step kernel will use): a neighbour on the far side of a
-    // piece boundary is that piece's own first / last sample.  Roots are LOCATED in fp32 -- a 4-sample
-    // window absorbs the location error -- candidates are EVALUATED in fp64.
+    // --- extremal samples of every piece (np.min / np.max of wind.py:87-89): lane (cv, sub) owns piece sub of curve cv ---
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     double mn = inf, mx = -inf;
     if (cv < nc && sub < np) {
         const double *cf = coef + (cv * np + sub) * 4;
-        const double k0 = cf[0], k1 = cf[1], k2 = cf[2], k3 = cf[3];
-        const int first = __ldg(c.piece_bounds + 2 * sub), last = __ldg(c.piece_bounds + 2 * sub + 1);
-        const int r_base = sub * c.Lm1;
-        const bool has_samples = first <= last;  // a table shorter than the spline can leave a piece without samples
-        auto consider = [&](int index) {
-            if (!has_samples) return;
-            index = max(first, min(index, last));
-            const double sl = (double)(index * np - r_base) * c.inv_Lm1;
-            const double v = fma(fma(fma(k3, sl, k2), sl, k1), sl, k0);
-            mn = (v < mn) ? v : mn;  // no NaNs here: plain compares instead of fmin / fmax
-            mx = (v > mx) ? v : mx;
-        };
-        consider(first);
-        consider(last);
-        const float A = 3.0f * (float)k3, B = 2.0f * (float)k2, C0 = (float)k1;
-        const float nanf_ = __int_as_float(0x7fc00000);
-        float s1 = nanf_, s2 = nanf_;
-        if (fabsf(A) > 1e-6f * (fabsf(B) + fabsf(C0))) {
-            const float disc = fmaf(B, B, -4.0f * A * C0);
-            if (disc >= 0.0f) {
-                const float q = -0.5f * (B + copysignf(sqrtf(disc), B));
-                s1 = __fdividef(q, A);
-                if (q != 0.0f) s2 = __fdividef(C0, q);
-            }
-        } else if (B != 0.0f) {
-            s1 = __fdividef(-C0, B);
-        }
-        const float per_piece = c.per_piece, margin = 3.0f * c.inv_per_piece;
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {
-            const float sr = which ? s2 : s1;
-            if (sr > -margin && sr < 1.0f + margin) {
-                const int f = (int)floorf(((float)sub + sr) * per_piece);
-                consider(f - 1);
-                consider(f);
-                consider(f + 1);
-                consider(f + 2);
-            }
-        }
+        piece_extremes(c, sub, cf[0], cf[1], cf[2], cf[3], mn, mx);
     }
     // segmented reduction: each half-warp reduces its own curve
 #pragma unroll
@@ -151,18 +179,72 @@ static __device__ __noinline__ void wind_setup_warp(const DevCfg &c, long long e
     if (lane < 4 * nc) {
         const int curve = lane >> 2, m = lane & 3;
         const double cfm = coef[(curve * np + jn) * 4 + m];
-        const double lo = curve ? mnB : mn, hi = curve ? mxB : mx;
-        double off = 0.0, inv = 1.0;
-        if (lo < 0.0 || hi > 1.0) { off = lo; inv = 1.0 / (hi - lo); }
-        // exp 4 / 6: curve * max_velocity (wind.py:49,62); exp 5: the rect threshold acts on the curve
-        // itself; second curve of exp 6: curve * pi * 2 (wind.py:63)
-        const double scale = curve ? 3.14159265358979323846 * 2.0
-                                   : ((c.wind_kind == WIND_ANGLE_RECT) ? 1.0 : c.p.max_velocity);
-        scratch[lane] = ((m == 0) ? (cfm - off) : cfm) * inv * scale;
+        scratch[lane] = fold_coef(c, curve, m, cfm, curve ? mnB : mn, curve ? mxB : mx);
     } else if (lane < 8) {
         scratch[lane] = 0.0;
     }
     __syncwarp();
+}
+
+// Lane-parallel mapping: ONE ENV PER LANE, no cooperation, no shared memory -- for the kernels whose setup work is
+// dense (reset of every env, the compacted episode-end queue of the K > 1 step kernels).  ~30 x fewer warp
+// instructions per env than the cooperative mapping (which keeps 14-16 of 32 lanes busy through five
+// __syncwarp-separated phases).  out[0..3]: folded coefficients of the first drawn curve's piece containing sample
+// index_next, out[4..7]: the second curve's (zeros when the experiment draws fewer curves).  FP = fixed_points as a
+// compile-time constant (8: the reference's default, everything in registers) or 0 (any value up to kMaxKnots).
+template <int FP>
+__device__ __forceinline__ void wind_setup_lane(const DevCfg &c, long long env_local, uint32_t episode, int index_next,
+                                                double (&out)[8]) {
+    const int fp = FP ? FP : c.fp, np = fp - 1, nc = c.ncurves;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    int jn, rn;
+    piece_of(c, min(index_next, c.L - 1), jn, rn);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) out[q] = 0.0;
+    const long long genv = c.env_id_offset + env_local;
+#pragma unroll
+    for (int curve = 0; curve < 2; ++curve) {
+        if (curve >= nc) break;
+        double u[FP ? FP : kMaxKnots];
+        if (c.ovr_knots) {
+#pragma unroll
+            for (int k = 0; k < (FP ? FP : kMaxKnots); ++k)
+                if (k < fp) u[k] = c.ovr_knots[env_local * 2 * fp + curve * fp + k];
+        } else if (FP == 8) {  // knots 8*curve .. 8*curve+7 = Philox blocks 2*curve+1, 2*curve+2 (episode_knot's layout)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const Philox4 r = philox4x32_10((uint32_t)genv, (uint32_t)((unsigned long long)genv >> 32), episode,
+                                                kStreamEpisode | (uint32_t)(1 + 2 * curve + b), (uint32_t)c.seed,
+                                                (uint32_t)(c.seed >> 32));
+                u[4 * b + 0] = knot_from_word(r.x);
+                u[4 * b + 1] = knot_from_word(r.y);
+                u[4 * b + 2] = knot_from_word(r.z);
+                u[4 * b + 3] = knot_from_word(r.w);
+            }
+        } else {
+            for (int k = 0; k < fp; ++k) u[k] = episode_knot(c.seed, genv, episode, curve * fp + k);
+        }
+        double mn = inf, mx = -inf, sel[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+        for (int j = 0; j < np; ++j) {
+            double cf[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) cf[m] = coef_dot(c.basis + (size_t)(j * 4 + m) * fp, u, fp);
+            piece_extremes(c, j, cf[0], cf[1], cf[2], cf[3], mn, mx);
+            if (j == jn) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) sel[m] = cf[m];
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) out[curve * 4 + m] = fold_coef(c, curve, m, sel[m], mn, mx);
+    }
+}
+
+__device__ __forceinline__ void wind_setup_lane_any(const DevCfg &c, long long env_local, uint32_t episode, int index_next,
+                                                    double (&out)[8]) {
+    if (c.fp == 8) wind_setup_lane<8>(c, env_local, episode, index_next, out);
+    else wind_setup_lane<0>(c, env_local, episode, index_next, out);
 }
 
 // np.random.randint draw of an episode (boat_env.py:147-150): only experiment 2 uses it.

@@ -206,3 +206,63 @@ def test_world_size_2_gloo_all_reduce(S, tmp_path):
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "GLOO_OK" in r.stdout
+
+
+_PBT_WORKER = """
+import random, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from sac_agent_b200 import population as P
+from sac_agent_b200.sharding import dist_info
+rank, local_rank, world = dist_info()
+dist.init_process_group("gloo", rank=rank, world_size=world)
+# member r: weights filled with r, an int64 step counter, its own hyper-parameters; rank 1 has the better score
+tensors = [torch.full((3, 4), float(rank)), torch.full((5,), 10.0 * rank), torch.tensor([100 + rank, 7], dtype=torch.int64)]
+hp = dict(alpha=0.002 + 0.004 * rank, beta=0.001 + 0.002 * rank, gamma=0.97, tau=0.005)
+new_hp, info = P.exploit_explore(tensors, hp, score=[-500.0, -100.0][rank], rng=random.Random(5), bottom_fraction=0.25)
+assert info["ranking"] == [1, 0] and info["scores"] == [-500.0, -100.0], info
+if rank == 0:   # the loser adopted member 1's state and a perturbed copy of its hyper-parameters
+    assert info["adopted_from"] == 1
+    assert torch.equal(tensors[0], torch.ones(3, 4)) and torch.equal(tensors[1], torch.full((5,), 10.0))
+    assert tensors[2].tolist() == [101, 7] and tensors[2].dtype == torch.int64
+    for k, (lo, hi) in P.HP_RANGES.items():
+        assert lo <= new_hp[k] <= hi
+    assert new_hp["alpha"] in (round(0.006 * 0.8, 4), round(0.006 * 1.25, 4)), new_hp
+    assert new_hp["gamma"] in (round(1 - 0.03 * 0.8, 4), round(1 - 0.03 * 1.25, 4)), new_hp
+else:           # the winner is untouched
+    assert info["adopted_from"] is None and new_hp == hp and torch.equal(tensors[0], torch.ones(3, 4))
+# a round in which nobody finished an episode changes nothing
+hp2, info2 = P.exploit_explore(tensors, new_hp, score=float("nan"), rng=random.Random(6))
+assert info2["adopted_from"] is None and hp2 == new_hp
+dist.barrier()
+if rank == 0:
+    print("PBT_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_population_exploit_explore_world_size_2_gloo(S, tmp_path):
+    """the exploit / explore round of population-based training on two gloo ranks."""
+    script = tmp_path / "pbt_worker.py"
+    script.write_text(_PBT_WORKER.format(root=ROOT))
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "PBT_OK" in r.stdout
+
+
+def test_population_perturb_stays_in_the_tuner_ranges():
+    import random
+    sys.path.insert(0, ROOT)
+    from sac_agent_b200 import population as P
+    rng = random.Random(0)
+    hp = dict(alpha=0.01, beta=0.0008, gamma=0.99, tau=0.001)
+    for _ in range(50):
+        hp = P.perturb(hp, rng)
+        for k, (lo, hi) in P.HP_RANGES.items():
+            assert lo <= hp[k] <= hi and round(hp[k], 4) == hp[k]

@@ -314,3 +314,56 @@ def test_fp32_exact_carriers_field_round_trip(S):
     _, _, done, info = env.step(a)
     assert info["term"][:3].tolist() == [0, 0, 5] and done[:3].tolist() == [0, 0, 1]
     env.close()
+
+
+def _wind_coefficients(env):
+    """[n_envs, 2, 4] wind piece coefficients of every env, cut out of the state blob (layout: common.cuh)."""
+    import torch
+    fp32 = env.precision == 32
+    nd_bytes = 32 * 16 * (2 if fp32 else 4)
+    w_bytes = 32 * 16 * (1 if fp32 else 2)
+    off_wa, off_wb = nd_bytes + 128, nd_bytes + 128 + w_bytes
+    block = off_wb + w_bytes + 128
+    nblk = (env.n_envs + 31) // 32
+    blob = env.state_dict()["blob"][: nblk * block].reshape(nblk, block)
+    out = []
+    for off in (off_wa, off_wb):
+        sec = blob[:, off:off + w_bytes].contiguous()
+        if fp32:
+            c = sec.view(torch.float32).reshape(nblk, 32, 4)
+        else:   # two 16-byte vector rows per lane: scalars (0, 1) in row 0, (2, 3) in row 1
+            c = sec.view(torch.float64).reshape(nblk, 2, 32, 2).permute(0, 2, 1, 3).reshape(nblk, 32, 4)
+        out.append(c.reshape(nblk * 32, 4)[: env.n_envs])
+    return torch.stack(out, dim=1)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_lane_parallel_and_cooperative_wind_setup_agree_bit_for_bit(S, precision):
+    """The reset kernel and the K > 1 episode-end queue kernel set the wind up one env per LANE, the K = 1 step kernel
+    one env per WARP (setup warps): same knots -> bit-identical piece coefficients, whatever path started the
+    episode.  (Every episode of an env is given the same knots through the validation override.)"""
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    n = 5000
+    rng = np.random.default_rng(3)
+    knots = (rng.integers(1, 2 ** 23, size=(n, 2, 8)) * 2 + 1) / 2.0 ** 24        # like knot_from_word: (2k+1) 2^-24
+    envs = {}
+    for name in ("reset", "k1", "k8"):
+        e = S.BatchedBoatEnv(cfg, n, seed=4, precision=precision, device=0, auto_reset=True)
+        e.set_episode_draws(None, knots)
+        e.reset()
+        envs[name] = e
+    base = _wind_coefficients(envs["reset"])                                      # lane-parallel (reset kernel)
+    assert torch.isfinite(base).all() and float(base.abs().max()) > 0
+    big = envs["k1"].uniform_actions(0, 40.0).clone()                              # |a| / 10 > pi/3 for most envs: rudder breaks at once
+    _, _, d1, _ = envs["k1"].step(big)                                             # in-kernel reset: cooperative (setup warps)
+    _, _, d8, _ = envs["k8"].step_k(torch.stack([big, big, big]), 3)               # deferred queue: lane-parallel
+    assert int(d1.sum()) > n // 2 and int(d8.sum()) >= int(d1.sum())
+    c1, c8 = _wind_coefficients(envs["k1"]), _wind_coefficients(envs["k8"])
+    assert torch.equal(c1, base) and torch.equal(c8, base)
+    # and they are the coefficients of the oracle's curve: wind[0] = c0 of piece 0
+    wv, wa = envs["reset"].wind_table(17)
+    assert abs(float(base[17, 0, 0]) - wv[0]) <= (1e-6 if precision == "fp32" else 1e-13)
+    assert abs(float(base[17, 1, 0]) - wa[0]) <= (1e-5 if precision == "fp32" else 1e-12)
+    for e in envs.values():
+        e.close()

@@ -56,8 +56,10 @@ def experiment_dir(tmp_path, name):
     return types.SimpleNamespace(experiment_dir=str(d))
 
 
-def run_loop(env, agent, recorder, steps, on_learn=None):
-    """main.py:70-99 without the progress table: one list entry per env step."""
+def run_loop(env, agent, recorder, steps, action_dtype=None):
+    """main.py:70-99 without the progress table: one list entry per env step.  action_dtype = np.float64 widens the
+    agent's float32 action before env.step (with a float32 action the reference's own
+    `rudder_angle += action[0] / 10` runs in float32, `0 + np.float32` stays float32)."""
     log = []
     episode = 0
     observation = env.reset()
@@ -72,10 +74,10 @@ def run_loop(env, agent, recorder, steps, on_learn=None):
             recorder.create_csvs(episode)
         recorder.write_data_to_csv()
         action = agent.choose_action(observation)
+        if action_dtype is not None:
+            action = np.asarray(action, dtype=action_dtype)
         observation_, reward, done, info = env.step(action)
         agent.remember(observation, action, reward, observation_, info["termination"] == "reached_goal")
-        if on_learn is not None:
-            on_learn()
         agent.learn()
         log.append((np.asarray(observation_, dtype=np.float64).copy(), float(reward), bool(done),
                     np.asarray(action, dtype=np.float64).copy(), float(env.boat.rudder_angle)))
@@ -85,7 +87,12 @@ def run_loop(env, agent, recorder, steps, on_learn=None):
     return log, episode
 
 
-def test_reference_agent_and_recorder_drive_the_drop_in(S, R, tmp_path):
+@pytest.mark.parametrize("action_dtype,tol", [(np.float64, 1e-6), (None, 2e-5)])
+def test_reference_agent_and_recorder_drive_the_drop_in(S, R, tmp_path, action_dtype, tol):
+    """action_dtype None: the loop exactly as main.py runs it -- the agent's float32 actions make the REFERENCE env
+    accumulate its rudder in float32 (H4), so it drifts ~1e-7 rad from the drop-in's fp64 rudder and the yaw
+    acceleration follows at ~1e-6: tolerance 2e-5.  np.float64: the same loop with the action widened first (the
+    parity convention of SURVEY.md 8c): both envs compute in fp64 and agree to the float32 policy's rounding."""
     import pandas as pd
     import torch
     cfg = R.load_config(base_settings__experiment=6, agent__batch_size=BATCH, agent__max_size=4096)
@@ -108,7 +115,7 @@ def test_reference_agent_and_recorder_drive_the_drop_in(S, R, tmp_path):
     torch.manual_seed(1234)
     agent_b = AgentB(config=cfg, experiment_dir=exp_b.experiment_dir, input_dims=env_b.observation_space.shape, env=env_b)
     assert type(agent_b.memory).__mro__[1] is S.ReplayBuffer
-    log_b, episodes_b = run_loop(env_b, agent_b, Recorder(env_b), STEPS)
+    log_b, episodes_b = run_loop(env_b, agent_b, Recorder(env_b), STEPS, action_dtype)
 
     # ---- run A: the reference env and buffer, same draws, same torch seed, same batch indices ----------------
     AgentA = R.import_reference_agent()
@@ -145,7 +152,7 @@ def test_reference_agent_and_recorder_drive_the_drop_in(S, R, tmp_path):
         env_a = ref.BoatEnv(cfg, exp_a)
         torch.manual_seed(1234)
         agent_a = AgentA(config=cfg, experiment_dir=exp_a.experiment_dir, input_dims=env_a.observation_space.shape, env=env_a)
-        log_a, episodes_a = run_loop(env_a, agent_a, Recorder(env_a), STEPS)
+        log_a, episodes_a = run_loop(env_a, agent_a, Recorder(env_a), STEPS, action_dtype)
     finally:
         np.random.randint, np.random.sample, np.random.choice = real_randint, real_sample, real_choice
 
@@ -154,12 +161,12 @@ def test_reference_agent_and_recorder_drive_the_drop_in(S, R, tmp_path):
     assert len(sampled) == STEPS - BATCH + 1 and next(replay, None) is None     # learn() ran from step 64 on, in both
     for t, (a, b) in enumerate(zip(log_a, log_b)):
         assert a[2] == b[2], f"done differs at step {t}"
-        assert np.abs(a[3] - b[3]).max() <= 1e-6, f"actions differ at step {t}"        # float32 policy outputs
-        assert np.abs(a[0] - b[0]).max() <= 1e-6 and abs(a[1] - b[1]) <= 1e-6 * max(1.0, abs(a[1])), t
-        assert abs(a[4] - b[4]) <= 1e-7
+        assert np.abs(a[3] - b[3]).max() <= tol, f"actions differ at step {t}"        # float32 policy outputs
+        assert np.abs(a[0] - b[0]).max() <= tol and abs(a[1] - b[1]) <= tol * max(1.0, abs(a[1])), t
+        assert abs(a[4] - b[4]) <= tol                                                    # env.boat.rudder_angle
     # before learning starts the actions are bit-identical, and so are the fp64 observations to 1e-9
     for a, b in zip(log_a[:BATCH - 1], log_b[:BATCH - 1]):
-        assert np.array_equal(a[3], b[3]) and np.abs(a[0] - b[0]).max() <= 1e-9
+        assert np.array_equal(a[3], b[3]) and np.abs(a[0] - b[0]).max() <= (1e-9 if action_dtype is not None else tol)
     assert env_a.info["termination"] == env_b.info["termination"]
     for k in ("reached_goal", "out_of_bounds", "out_of_fuel", "rudder_broken", "timeout"):
         assert env_a.info[k] == env_b.info[k]
@@ -167,9 +174,9 @@ def test_reference_agent_and_recorder_drive_the_drop_in(S, R, tmp_path):
     ma, mb = agent_a.memory, agent_b.memory
     assert ma.mem_cntr == mb.mem_cntr == STEPS and ma.mem_size == mb.mem_size == 4096
     s, a_, r, s2, d = S.ReplayBuffer.gather(mb, np.arange(STEPS), as_torch=False)
-    assert np.abs(s - ma.state_memory[:STEPS]).max() <= 1e-6 and np.abs(s2 - ma.new_state_memory[:STEPS]).max() <= 1e-6
-    assert np.abs(a_ - ma.action_memory[:STEPS]).max() <= 1e-6 and np.array_equal(d, ma.terminal_memory[:STEPS])
-    assert np.abs(r - ma.reward_memory[:STEPS]).max() <= 1e-6 * np.maximum(1.0, np.abs(ma.reward_memory[:STEPS])).max()
+    assert np.abs(s - ma.state_memory[:STEPS]).max() <= tol and np.abs(s2 - ma.new_state_memory[:STEPS]).max() <= tol
+    assert np.abs(a_ - ma.action_memory[:STEPS]).max() <= tol and np.array_equal(d, ma.terminal_memory[:STEPS])
+    assert np.abs(r - ma.reward_memory[:STEPS]).max() <= tol * np.maximum(1.0, np.abs(ma.reward_memory[:STEPS])).max()
     # the networks were trained identically (same batches, same code: the reference's learn())
     for pa, pb in zip(agent_a.actor.parameters(), agent_b.actor.parameters()):
         assert torch.allclose(pa, pb, atol=1e-4, rtol=1e-3)
@@ -178,7 +185,8 @@ def test_reference_agent_and_recorder_drive_the_drop_in(S, R, tmp_path):
         fa = pd.read_csv(os.path.join(exp_a.experiment_dir, "episodes", f"episode_{e}_data.csv"), sep=";")
         fb = pd.read_csv(os.path.join(exp_b.experiment_dir, "episodes", f"episode_{e}_data.csv"), sep=";")
         assert list(fa.columns) == list(fb.columns) and len(fa) == len(fb)
-        assert np.abs(fa.values.astype(np.float64) - fb.values.astype(np.float64)).max() <= 1e-5
+        va, vb = fa.values.astype(np.float64), fb.values.astype(np.float64)                # raw metres / rad, not normalised
+        assert np.all(np.abs(va - vb) <= 10 * tol * np.maximum(1.0, np.abs(va)))
     ia = pd.read_csv(os.path.join(exp_a.experiment_dir, "episodes", "info.csv"), sep=";")
     ib = pd.read_csv(os.path.join(exp_b.experiment_dir, "episodes", "info.csv"), sep=";")
     assert list(ia.columns) == list(ib.columns) and list(ia.termination) == list(ib.termination)
