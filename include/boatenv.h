@@ -102,7 +102,8 @@ BOATENV_API int boatenv_reset(boatenv_t h, const uint8_t *mask, void *obs_out, v
  *   actions       T[n_envs]            (action[0] of each env; not clipped, like :73)
  *   obs_out       T[n_envs][11]        normalised state (:308-323)
  *   reward_out    T[n_envs]
- *   done_out      uint8[n_envs]
+ *   done_out      uint8[n_envs], or NULL when term_out is given (done == (term != 0): one byte per
+ *                 env-step of HBM writes less)
  *   term_out      uint8[n_envs] or NULL  BOATENV_TERM_* of this step
  *   final_obs_out T[n_envs][11] or NULL  written only where done (terminal observation)
  */

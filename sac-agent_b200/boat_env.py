@@ -128,17 +128,20 @@ class BatchedBoatEnv:
                                          self._stream()), "boatenv_reset")
         return self.obs
 
-    def step(self, actions):
+    def step(self, actions, done_from_term=False):
         """BoatEnv.step (boat_env.py:67-115) for every env.  Returns (obs, reward, done, info);
         info holds the per-env termination codes and, under auto-reset, the terminal
         observations of the envs that finished.  The returned tensors are the env's own output
-        buffers (no allocation per step): the next step overwrites them, clone what must survive."""
+        buffers (no allocation per step): the next step overwrites them, clone what must survive.
+        ``done_from_term``: the kernel writes only the termination codes and ``done`` is returned as None
+        (done == (info["term"] != 0)): one byte per env-step of HBM writes less."""
         a = self._actions(actions)
         flags = AUTO_RESET if self.auto_reset else 0
         _lib.check(self._L.boatenv_step(self._h, a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
-                                        self.done.data_ptr(), self.term.data_ptr(), self.final_obs.data_ptr(),
-                                        flags, self._stream()), "boatenv_step")
-        return self.obs, self.reward, self.done, {"term": self.term, "final_obs": self.final_obs}
+                                        None if done_from_term else self.done.data_ptr(), self.term.data_ptr(),
+                                        self.final_obs.data_ptr(), flags, self._stream()), "boatenv_step")
+        return (self.obs, self.reward, None if done_from_term else self.done,
+                {"term": self.term, "final_obs": self.final_obs})
 
     def step_k(self, actions, k, steps_out=None):
         """k fused sub-steps; ``actions`` is [k, N] or [N] (repeated)."""

@@ -237,8 +237,16 @@ static int derive_config(const boatenv_params *p, DevCfg &c) {
         f.sy_inv = (float)(1.0 / (double)(1LL << f.sy_shift));
         f.sx_goal = (int)std::ceil(p->goal_line * (double)(1LL << f.sx_shift));
         f.sy_oob = (int)std::floor((p->track_width + p->oob_offset) * (double)(1LL << f.sy_shift));
-        f.rud_pi3 = std::floor((PI / 3.0) * 4398046511104.0);
-        f.rud_pi4 = std::floor((PI / 4.0) * 4398046511104.0);
+        f.sy_oob2 = 2u * (unsigned)f.sy_oob;
+        {   // the bit patterns of the two rudder thresholds (common.cuh) are those of the doubles
+            unsigned long long b3, b4;
+            const double d3 = kRudPi3, d4 = kRudPi4;
+            std::memcpy(&b3, &d3, 8);
+            std::memcpy(&b4, &d4, 8);
+            if (b3 != kRudPi3Bits || b4 != kRudPi4Bits) return BOATENV_EUNSUPPORTED;
+        }
+        if (std::floor((PI / 3.0) * 4398046511104.0) != kRudPi3 || std::floor((PI / 4.0) * 4398046511104.0) != kRudPi4)
+            return BOATENV_EUNSUPPORTED;   // the literals in common.cuh are these two numbers
         f.sx_obs = (float)(1.0 / (double)(1LL << f.sx_shift) / p->goal_line);
         f.sy_obs = (float)(1.0 / (double)(1LL << f.sy_shift) / (2.0 * p->track_width));
     }
@@ -378,7 +386,7 @@ int boatenv_reset(boatenv_t h, const uint8_t *mask, void *obs_out, void *stream)
 static int step_common(boatenv_t h, StepArgs &a, cudaStream_t st) {
     if (!h->was_reset) return BOATENV_ESTATE;
     a.reverse = (int)(h->launch_parity++ & 1u);
-    if (!a.actions || !a.obs_out || !a.reward_out || !a.done_out || a.ksteps < 1) return BOATENV_EINVAL;
+    if (!a.actions || !a.obs_out || !a.reward_out || (!a.done_out && !a.term_out) || a.ksteps < 1) return BOATENV_EINVAL;
     if (!aligned16(a.obs_out)) return BOATENV_EALIGN;
     GUARD_DEVICE(h);
     CUDA_TRY(h->precision == 32 ? launch_step_f32(h->cfg, a, st) : launch_step_f64(h->cfg, a, st));

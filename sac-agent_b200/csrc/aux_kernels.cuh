@@ -46,14 +46,14 @@ __global__ void __launch_bounds__(kTile, LANE ? 2 : 4) boat_reset_kernel(const _
     const int sy0 = episode_start_y(c, i, e_epi);  // boat_env.py:166-167
     Fx<T> fx;
     fx.start(c, d, sy0);
-    fx.pack(d);
+    const uint32_t index_word = fx.pack(d, 0);
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         wa[m] = (T)w8[m];
         wb[m] = (T)w8[4 + m];
     }
     store_vecs<T, D_COUNT>(block_section(c, i, 0), lane, d);
-    *index_ptr(c, i) = fx.index_word(0);
+    *index_ptr(c, i) = index_word;
     *episode_ptr(c, i) = e_epi;
     if (c.ncurves >= 1) store_vecs<T, 4>(block_section(c, i, c.off_wa), lane, wa);
     if (c.ncurves >= 2) store_vecs<T, 4>(block_section(c, i, c.off_wb), lane, wb);

@@ -62,7 +62,7 @@ __device__ __forceinline__ void fast_sincosf(float x, float &s, float &c) {
 // wind[index].  Updates d[], returns the three accelerations (they are observations),
 // the reward and the termination code.
 // ---------------------------------------------------------------------------------
-template <int WK>
+template <int WK, bool SAT>
 __device__ __forceinline__ void substep(const DevCfg &c, double (&d)[D_COUNT], Fx<double> &, int index, double action,
                                         double w, double th, double (&acc)[3], double &reward, int &code) {
     // fp64 validation mode: the reference's own operation order (Python's a*b*c is
@@ -136,7 +136,7 @@ __device__ __forceinline__ void substep(const DevCfg &c, double (&d)[D_COUNT], F
     d[D_SX] = s_x; d[D_SY] = s_y; d[D_SR] = s_r; d[D_RET] += r;  // :113
 }
 
-template <int WK>
+template <int WK, bool SAT>
 __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], Fx<float> &fx, int index, float action,
                                         float w, float th, float (&acc)[3], float &reward, int &code) {
     // fp32 production mode: config products folded on the host (FastConsts); the
@@ -160,8 +160,10 @@ __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], Fx
         const double t = fma((double)a_c, 4398046511104.0 / 10.0, 6755399441055744.0);
         fx.rud += t - 6755399441055744.0;
     }
-    const double rud_abs = fabs(fx.rud);
-    const bool rud_broken = rud_abs > f.rud_pi3, rud_penalty = rud_abs > f.rud_pi4;
+    // |rud| > threshold on the bit pattern (non-negative doubles order like their 64-bit patterns): integer
+    // compares against immediates, no 64-bit constants to materialise inside the K loop
+    const unsigned long long rud_abs = (unsigned long long)__double_as_longlong(fx.rud) & 0x7fffffffffffffffull;
+    const bool rud_broken = rud_abs > kRudPi3Bits, rud_penalty = rud_abs > kRudPi4Bits;
     float v_x = d[D_VX], v_y = d[D_VY], v_r = d[D_VR];
 
     float F_Wx = 0.0f, F_Wy = 0.0f;
@@ -194,8 +196,8 @@ __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], Fx
     const float s_r = fmaf(v_r, f.dt, d[D_SR]);
     float sr, cr;
     fast_sincosf(s_r, sr, cr);
-    fx.sx = add_sat_s32(fx.sx, fixed_increment(fmaf(v_x, cr, -v_y * sr), f.sx_k));
-    fx.sy = add_sat_s32(fx.sy, fixed_increment(fmaf(v_y, cr, v_x * sr), f.sy_k));
+    fx.sx = add_fixed<SAT>(fx.sx, fixed_increment(fmaf(v_x, cr, -v_y * sr), f.sx_k));
+    fx.sy = add_fixed<SAT>(fx.sy, fixed_increment(fmaf(v_y, cr, v_x * sr), f.sy_k));
     const float s_y = (float)fx.sy * f.sy_inv;   // the float view of s_x is only needed for the observation (stage_obs)
     const float ay = fabsf(s_y);
     float r = -__fdividef(ay * f.rew_inv_W, 1.0f + __expf(f.rew_k * (ay - f.rew_y0)));
@@ -206,7 +208,8 @@ __device__ __forceinline__ void substep(const DevCfg &c, float (&d)[D_COUNT], Fx
     code = rud_broken ? BOATENV_TERM_RUDDER_BROKEN : BOATENV_TERM_NONE;
     code = (index + 1 >= c.timeout_steps) ? BOATENV_TERM_TIMEOUT : code;
     code = (index + 1 >= c.fuel_steps) ? BOATENV_TERM_OUT_OF_FUEL : code;
-    code = (fx.sy > f.sy_oob || fx.sy < -f.sy_oob || fx.sx < 0) ? BOATENV_TERM_OUT_OF_BOUNDS : code;
+    // abs(s_y) > W + offset or s_x < 0 (:90): |sy| > sy_oob <=> (unsigned)(sy + sy_oob) > 2 sy_oob; sign bit of sx
+    code = ((unsigned)fx.sy + (unsigned)f.sy_oob > f.sy_oob2 || fx.sx < 0) ? BOATENV_TERM_OUT_OF_BOUNDS : code;
     code = goal ? BOATENV_TERM_REACHED_GOAL : code;
     r += goal ? 1000.0f : 0.0f;
     if (rud_penalty) r = fmaf(-100.0f, ar, r);
@@ -625,9 +628,9 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
             T dd[D_COUNT];
 #pragma unroll
             for (int q = 0; q < D_COUNT; ++q) dd[q] = d[q];
-            fx.pack(dd);
+            const uint32_t index_word = fx.pack(dd, index);
             store_vecs<T, D_COUNT>(gb, lane, dd);
-            st_state(reinterpret_cast<uint32_t *>(gb + c.off_idx) + lane, fx.index_word(index));
+            st_state(reinterpret_cast<uint32_t *>(gb + c.off_idx) + lane, index_word);
         };
         // state + per-env outputs of this launch (K = 1: right after the sub-step; K > 1: after the loop)
         auto store_results = [&]() {
@@ -641,7 +644,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
                 }
 #ifndef BOAT_DEBUG_SKIP_SMALL
                 __stcs(reinterpret_cast<T *>(a.reward_out) + i, rsum);
-                a.done_out[i] = (code != BOATENV_TERM_NONE) ? 1 : 0;
+                if (a.done_out) a.done_out[i] = (code != BOATENV_TERM_NONE) ? 1 : 0;   // NULL: the caller reads done = (term != 0)
                 if (a.term_out) a.term_out[i] = (uint8_t)code;
 #endif
                 if (KMULTI) {
@@ -652,13 +655,16 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
 
         // per-sub-step actions ([K][N] layout): the action of sub-step k + 1 is fetched while sub-step k computes
         const bool per_substep = KMULTI && a.action_stride != 0;
-        const T *act_i = act + min(i, n_end - 1);
+        // the pointer walks one row of the [K][N] action matrix per sub-step (no 64-bit multiply in the loop);
+        // with a repeated action (stride 0) it stays where it is and re-reads the same, cached, element
+        const T *act_next = act + min(i, n_end - 1) + (size_t)a.action_stride;
         T action_k1 = action;
-        if (per_substep && ksteps > 1) action_k1 = __ldcs(act_i + (size_t)a.action_stride);
+        if (per_substep && ksteps > 1) action_k1 = __ldcs(act_next);
         for (int k = 0; k < ksteps; ++k) {
             if (KMULTI && k > 0) {
                 action = action_k1;
-                if (per_substep && k + 1 < ksteps) action_k1 = __ldcs(act_i + (size_t)(k + 1) * (size_t)a.action_stride);
+                act_next += (size_t)a.action_stride;
+                if (per_substep && k + 1 < ksteps) action_k1 = __ldcs(act_next);
             }
             bool need_setup = false;
             if (alive) {
@@ -688,7 +694,7 @@ boat_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ StepA
 #ifdef BOAT_DEBUG_NOCOMPUTE  // memory-pattern experiment only: stream the state through untouched
                 acc[0] = acc[1] = acc[2] = w + th; rew = action; code = BOATENV_TERM_NONE;
 #else
-                substep<WK>(c, d, fx, index, action, w, th, acc, rew, code);
+                substep<WK, !KMULTI>(c, d, fx, index, action, w, th, acc, rew, code);
 #endif
                 rsum += rew;
                 ++nsteps;

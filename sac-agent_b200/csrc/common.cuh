@@ -62,7 +62,7 @@ struct FastConsts {
     int sx_shift, sy_shift;
     int sx_goal;                        // s_x >= goal_line        <=> sx >= sx_goal   (boat_env.py:85)
     int sy_oob;                         // abs(s_y) > W + offset   <=> |sy| > sy_oob   (boat_env.py:90)
-    double rud_pi3, rud_pi4;            // abs(rudder) > pi/3, pi/4 <=> |rud| > rud_pi3, rud_pi4 (boat_env.py:102,107)
+    unsigned sy_oob2;                   // 2 * sy_oob
     float sx_obs, sy_obs;               // 2^-sx_shift / goal_line, 2^-sy_shift / (2 W): fixed point -> normalised observation
 };
 
@@ -214,9 +214,16 @@ constexpr int kRudLoBits = 12;           // low bits of the rudder stored beside
 constexpr int kIndexBits = 20;           // step index: bits 0..19 of the index word (L <= 2^20 - 64)
 constexpr uint32_t kIndexMask = (1u << kIndexBits) - 1u;
 constexpr long long kRudLimit = (1LL << 43) - 1;   // |rudder| saturates just below 2 rad
+// abs(rudder) > pi/3, pi/4 (boat_env.py:102,107) <=> |rud| > floor(fp64(pi/3) * 2^42), floor(fp64(pi/4) * 2^42)
+constexpr double kRudPi3 = 4605623536476.0, kRudPi4 = 3454217652357.0;
+constexpr unsigned long long kRudPi3Bits = 0x4290C152382D7000ull, kRudPi4Bits = 0x428921FB54442800ull;  // their bit patterns
 
 #ifdef __CUDACC__
-__device__ __forceinline__ int add_sat_s32(int a, int b) {
+// position accumulation: saturating (5 instructions) in the K = 1 kernels, where an env that was not reset after
+// its episode ended can be stepped on and on; plain (1 instruction) in the issue-bound K > 1 kernels, where an env
+// stops at its first done inside a window.  Identical wherever nothing overflows.
+template <bool SAT> __device__ __forceinline__ int add_fixed(int a, int b) {
+    if (!SAT) return a + b;
     int r;
     asm("add.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
     return r;
@@ -225,8 +232,7 @@ __device__ __forceinline__ int add_sat_s32(int a, int b) {
 template <typename T> struct Fx;
 template <> struct Fx<double> {
     __device__ __forceinline__ void load(const DevCfg &, const double (&)[D_COUNT], uint32_t ixw, int &index) { index = (int)(ixw & kIndexMask); }
-    __device__ __forceinline__ void pack(double (&)[D_COUNT]) const {}
-    __device__ __forceinline__ uint32_t index_word(int index) const { return (uint32_t)index; }
+    __device__ __forceinline__ uint32_t pack(double (&)[D_COUNT], int index) const { return (uint32_t)index; }
     __device__ __forceinline__ void start(const DevCfg &, double (&d)[D_COUNT], int s_y0) {  // Boat.__init__ boat_env.py:144-201
 #pragma unroll
         for (int q = 0; q < D_COUNT; ++q) d[q] = 0.0;
@@ -247,14 +253,14 @@ template <> struct Fx<float> {
     __device__ __forceinline__ long long rud_bits() const {   // saturated to the 44 stored bits
         return __double2ll_rn(fmin(fmax(rud, -(double)kRudLimit), (double)kRudLimit));
     }
-    // the bit patterns that go to HBM (d keeps its float views; call on a copy or right before the store)
-    __device__ __forceinline__ void pack(float (&d)[D_COUNT]) const {
-        d[D_RUDDER] = __int_as_float((int)(rud_bits() >> kRudLoBits));
+    // the bit patterns that go to HBM (d keeps its float views; call on a copy or right before the store);
+    // returns the step-index word (the index and the low rudder bits)
+    __device__ __forceinline__ uint32_t pack(float (&d)[D_COUNT], int index) const {
+        const long long q = rud_bits();
+        d[D_RUDDER] = __int_as_float((int)(q >> kRudLoBits));
         d[D_SX] = __int_as_float(sx);
         d[D_SY] = __int_as_float(sy);
-    }
-    __device__ __forceinline__ uint32_t index_word(int index) const {
-        return (uint32_t)index | (((uint32_t)rud_bits() & ((1u << kRudLoBits) - 1u)) << kIndexBits);
+        return (uint32_t)index | (((uint32_t)q & ((1u << kRudLoBits) - 1u)) << kIndexBits);
     }
     __device__ __forceinline__ float rudder_view() const { return (float)rud * 2.27373675443232059478759765625e-13f; }  // 2^-42
     __device__ __forceinline__ void start(const DevCfg &c, float (&d)[D_COUNT], int s_y0) {

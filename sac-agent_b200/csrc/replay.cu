@@ -286,7 +286,7 @@ int64_t boatreplay_mem_size(boatreplay_t r) { return r ? r->mem_size : BOATENV_E
 
 int boatenv_step_store(boatenv_t h, boatreplay_t r, const void *actions, void *obs_inout, void *reward_out,
                        uint8_t *done_out, uint8_t *term_out, int done_flag_mode, uint32_t flags, void *stream) {
-    if (!h || !r || !actions || !obs_inout || !reward_out || !done_out) return BOATENV_EINVAL;
+    if (!h || !r || !actions || !obs_inout || !reward_out || (!done_out && !term_out)) return BOATENV_EINVAL;
     if (!handle_was_reset(h)) return BOATENV_ESTATE;
     const DevCfg &c = *handle_cfg(h);
     if (handle_precision(h) != r->precision || handle_device(h) != r->device || r->obs_dim != kObsDim ||

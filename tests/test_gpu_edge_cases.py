@@ -367,3 +367,25 @@ def test_lane_parallel_and_cooperative_wind_setup_agree_bit_for_bit(S, precision
     assert abs(float(base[17, 1, 0]) - wa[0]) <= (1e-5 if precision == "fp32" else 1e-12)
     for e in envs.values():
         e.close()
+
+
+def test_done_can_be_derived_from_the_termination_codes(S):
+    """boatenv_step with done_out = NULL: only term_out is written, done == (term != 0); everything else is identical."""
+    import torch
+    cfg = S.load_config(base_settings__experiment=6)
+    a = S.BatchedBoatEnv(cfg, 20_000, seed=6, precision="fp32", device=0, auto_reset=True)
+    b = S.BatchedBoatEnv(cfg, 20_000, seed=6, precision="fp32", device=0, auto_reset=True)
+    a.reset(); b.reset()
+    b.done.fill_(77)
+    n_done = 0
+    for t in range(30):
+        acts = a.uniform_actions(t, 4.0)
+        o1, r1, d1, i1 = a.step(acts)
+        o2, r2, d2, i2 = b.step(acts, done_from_term=True)
+        assert d2 is None and torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(i1["term"], i2["term"])
+        assert torch.equal(d1, (i2["term"] != 0).to(torch.uint8))
+        n_done += int(d1.sum())
+    assert n_done > 0 and bool((b.done == 77).all())      # the done buffer was never written
+    L = a._L
+    assert L.boatenv_step(a._h, acts.data_ptr(), a.obs.data_ptr(), a.reward.data_ptr(), None, None, None, 1, None) == -1
+    a.close(); b.close()
