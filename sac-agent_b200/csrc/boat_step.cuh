@@ -78,10 +78,12 @@ __device__ __forceinline__ void substep(const DevCfg &c, double (&d)[D_COUNT], F
     double F_Wx = 0.0, F_Wy = 0.0;
     if (WK != WIND_NONE) {  // boat_env.py:230-236, 256-262
         const double sgn = (double)((w > 0.0) - (w < 0.0));
+        double sin_th, cos_th;
+        sincos(th, &sin_th, &cos_th);   // one argument reduction for both (same values as sin() / cos())
         F_Wx = w * w * sgn * p.c_r_front * 0.5 * p.rho * p.boat_area_front;
-        F_Wx = F_Wx * cos(th);
+        F_Wx = F_Wx * cos_th;
         F_Wy = w * w * sgn * p.c_r_side * 0.5 * p.rho * p.boat_area_side;
-        F_Wy = F_Wy * sin(th);
+        F_Wy = F_Wy * sin_th;
     }
     // eom_longitudinal  boat_env.py:213-239 (old v_x, v_y, v_r)
     double F_R = v_x * v_x * p.c_r_front * 0.5 * p.rho * p.boat_area_front;
@@ -113,8 +115,10 @@ __device__ __forceinline__ void substep(const DevCfg &c, double (&d)[D_COUNT], F
     const double drift = atan2(v_x, v_y);
     const double s_r = v_r * p.dt + d[D_SR];
     const double dir = drift - s_r;
-    const double s_x = sin(dir) * v * p.dt + d[D_SX];
-    const double s_y = cos(dir) * v * p.dt + d[D_SY];
+    double sin_dir, cos_dir;
+    sincos(dir, &sin_dir, &cos_dir);
+    const double s_x = sin_dir * v * p.dt + d[D_SX];
+    const double s_y = cos_dir * v * p.dt + d[D_SY];
     const double fuel = p.fuel - (double)(index + 1);  // boat_env.py:70
 
     // exponential_reward  reward_functions.py:42-57 with y_a = 0.03, y_b = 3.4 (boat_env.py:16-22)
