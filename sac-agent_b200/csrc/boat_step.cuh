@@ -336,7 +336,8 @@ template <> struct StepTuning<double, true> { static constexpr int kMinBlocks = 
 constexpr int kStages = BOAT_STAGES;
 
 #ifndef BOAT_SETUP_WARPS
-#define BOAT_SETUP_WARPS 4    // dedicated wind-setup warps per CTA in the K = 1 kernels of experiments 4-6
+#define BOAT_SETUP_WARPS 2    // dedicated wind-setup warps per CTA in the K = 1 kernels of experiments 4-6 (round-2 A/B on one
+                              // box, 16 M envs of exp 6: 1 warp 0.566 ms, 2 warps 0.4696, 4 warps 0.4750; profiles/jobs/r02y.sh)
 #endif
 // K = 1 kernels of the random-wind experiments run warp-specialised: 8 step warps stream the state
 // and push their (rare) wind-setup requests into a shared-memory queue, kSetup extra warps serve it.
