@@ -18,7 +18,11 @@
  *   - there is no CPU fallback: every compute entry point launches sm_100a kernels.
  *   - `precision` is 32 (production: fp32 state/obs, float actions) or 64
  *     (validation: fp64 in the reference's operation order, double actions).
- *     Element type T below means float or double accordingly.
+ *     Element type T below means float or double accordingly.  In the 32-bit mode everything a termination
+ *     threshold is applied to after accumulation is carried exactly in the same state bytes: the rudder angle
+ *     (boat_env.py:72-73, :102-108) as a 44-bit fixed-point number (2^-42 rad), s_x / s_y (:85-93) as int32 fixed
+ *     point; get/set_field and env_state_host exchange plain numbers.  Actions are clamped to +-64 before the
+ *     rudder update (no outcome changes: |action| >= 21 breaks the rudder from any unbroken state).
  */
 #ifndef BOATENV_H
 #define BOATENV_H
@@ -40,7 +44,7 @@ extern "C" {
 #define BOATENV_EEXPERIMENT (-2)   /* unknown experiment: the ValueError of wind.py:65-67   */
 #define BOATENV_EFIXEDPOINTS (-3)  /* fixed_points < 4: the ValueError of wind.py:73-75     */
 #define BOATENV_EUNSUPPORTED (-4)  /* valid for the reference, not for this build (e.g.
-                                      fixed_points > 16, t_max/dt > 2^20)                  */
+                                      fixed_points > 16, t_max/dt > 2^20 - 64)             */
 #define BOATENV_ENODEVICE (-5)     /* no CUDA device / not an sm_100 device                 */
 #define BOATENV_ESTATE (-6)        /* step() before reset()                                 */
 #define BOATENV_EALIGN (-7)        /* a tensor pointer is not 16-byte aligned               */

@@ -764,6 +764,7 @@ int boatenv_reduce_counters(boatenv_t h, double *out_device, void *stream) {
 
 int boatenv_get_counters(boatenv_t h, double *out_host, void *stream) {
     if (!h || !out_host) return BOATENV_EINVAL;
+    GUARD_DEVICE(h);   // the copy and the synchronise below run on the handle's device too
     int rc = boatenv_reduce_counters(h, h->counters_out_dev, stream);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_host, h->counters_out_dev, kNumCounters * sizeof(double), cudaMemcpyDeviceToHost,

@@ -389,3 +389,33 @@ def test_done_can_be_derived_from_the_termination_codes(S):
     L = a._L
     assert L.boatenv_step(a._h, acts.data_ptr(), a.obs.data_ptr(), a.reward.data_ptr(), None, None, None, 1, None) == -1
     a.close(); b.close()
+
+
+def test_abi_calls_leave_the_callers_device_alone(S):
+    """Every handle-based entry point switches to the handle's device and restores the caller's.  With one
+    visible GPU the handle lives on device 0 and the check is that nothing changes; with more, the handle lives on
+    device 1 while torch's current device stays 0 through create / reset / step / counters / replay / toy calls."""
+    import torch
+    dev = 1 if torch.cuda.device_count() > 1 else 0
+    torch.cuda.set_device(0)
+    cfg = S.load_config(base_settings__experiment=6)
+    env = S.BatchedBoatEnv(cfg, 5000, seed=1, precision="fp32", device=dev, auto_reset=True)
+    assert torch.cuda.current_device() == 0
+    with torch.cuda.device(dev):            # tensors and streams of the handle's device for the launches themselves
+        env.reset()
+        acts = env.uniform_actions(0, 2.0)
+        env.step(acts)
+        torch.cuda.synchronize()
+    assert torch.cuda.current_device() == 0
+    c = env.counters()                      # called with device 0 current: reduce + copy run on the handle's device
+    assert torch.cuda.current_device() == 0 and c["episodes"] >= 0
+    ring = S.ReplayBuffer(10_000, (11,), 1, precision="fp32", device=dev, as_torch=True)
+    toy = S.ToyCar(n_envs=64, precision="fp32", device=dev)
+    assert torch.cuda.current_device() == 0
+    with torch.cuda.device(dev):
+        ring.step_store(env, acts)
+        toy.step(3)
+        torch.cuda.synchronize()
+    assert torch.cuda.current_device() == 0 and ring.mem_cntr == 5000
+    env.close(); ring.close(); toy.close()
+    assert torch.cuda.current_device() == 0
