@@ -53,6 +53,8 @@ def main(argv=None):
                     help="population mode (main.py -p): every rank trains with its own tuned_configs.yaml draw")
     ap.add_argument("--policy-precision", default="fp32", choices=["fp32", "tf32", "bf16", "tcgen05"],
                     help="dense layers of choose_action on tensor-core inputs (acting only; the learner stays fp32)")
+    ap.add_argument("--set", action="append", default=[], metavar="SECTION__KEY=VALUE",
+                    help="override a config key, e.g. --set agent__learning_rate_alpha=0.001 (original_config.yaml names)")
     ap.add_argument("--pbt-every", type=int, default=0,
                     help="population-based training (with torchrun, one member per GPU): every this many iterations the "
                          "bottom quarter adopts the best member's weights + hyper-parameters and perturbs them")
@@ -65,7 +67,11 @@ def main(argv=None):
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.manual_seed(args.seed + rank)
-    cfg = S.load_config(base_settings__experiment=args.experiment)
+    overrides = {}
+    for item in args.set:
+        k, v = item.split("=", 1)
+        overrides[k] = float(v) if any(ch in v for ch in ".e") else int(v)
+    cfg = S.load_config(base_settings__experiment=args.experiment, **overrides)
     exp = None
     if args.experiments_root:   # utils/build_experiment.py: one experiment directory per population member
         import random
@@ -142,7 +148,7 @@ def main(argv=None):
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
     stats = S.all_reduce_counters(env.counters_tensor())
     sec = float(ms.item()) * 1e-3
-    summary = {"example": "train_sac", "n_gpus": world, "envs_total": args.envs, "iters": args.iters,
+    summary = {"example": "train_sac", "overrides": overrides, "n_gpus": world, "envs_total": args.envs, "iters": args.iters,
                "updates_per_iter": args.updates_per_iter, "cuda_graph": not args.no_graph, "overlap": bool(args.overlap),
                "policy_precision": args.policy_precision,
                "env_steps_per_s": args.iters * args.envs / sec,

@@ -18,6 +18,7 @@ from .config import load_config, params_from_config
 
 TERM_NAMES = ("", "reached_goal", "out_of_bounds", "out_of_fuel", "timeout", "rudder_broken")
 AUTO_RESET = 1
+STATE_FORMAT = 2   # layout of the opaque state blob: 2 = fp32 mode carries rudder / s_x / s_y in fixed point (common.cuh)
 FIELDS = {"v_x": 0, "v_y": 1, "v_r": 2, "rudder_angle": 3, "s_x": 4, "s_y": 5, "s_r": 6,
           "episode_reward": 7, "index": 8, "episode": 9}
 COUNTER_NAMES = ("reached_goal", "out_of_bounds", "out_of_fuel", "timeout", "rudder_broken",
@@ -259,12 +260,15 @@ class BatchedBoatEnv:
         torch = _torch()
         blob = torch.empty(int(self._L.boatenv_state_bytes(self._h)), dtype=torch.uint8, device=self.device)
         _lib.check(self._L.boatenv_export_state(self._h, blob.data_ptr(), self._stream()), "boatenv_export_state")
-        return {"blob": blob, "obs": self.obs.clone(), "n_envs": self.n_envs, "precision": self.precision,
+        return {"format": STATE_FORMAT, "blob": blob, "obs": self.obs.clone(), "n_envs": self.n_envs, "precision": self.precision,
                 "seed": self.seed, "env_id_offset": self.env_id_offset,
                 "params": bytes(memoryview(self.params).cast("B"))}
 
     def load_state_dict(self, sd):
         torch = _torch()
+        if sd.get("format", 1) != STATE_FORMAT:
+            raise ValueError(f"checkpoint state layout {sd.get('format', 1)} != {STATE_FORMAT} (the fp32 mode's rudder / position "
+                             "slots changed encoding in format 2)")
         for k in ("n_envs", "precision", "seed", "env_id_offset"):
             if sd[k] != getattr(self, k):
                 raise ValueError(f"checkpoint {k}={sd[k]!r} does not match this env ({getattr(self, k)!r})")

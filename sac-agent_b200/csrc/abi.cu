@@ -1,5 +1,6 @@
 // abi.cu -- the extern "C" front end of libboatenv.so (include/boatenv.h): handle
 // management, config derivation, launches.  No compute happens on the host.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
@@ -229,8 +230,12 @@ static int derive_config(const boatenv_params *p, DevCfg &c) {
             while (sh > 0 && reach * (double)(1LL << sh) >= 2147483647.0) --sh;
             return sh;
         };
-        f.sx_shift = shift_for(std::fabs(p->goal_line) * 1.02 + 16.0);
-        f.sy_shift = shift_for((std::fabs(p->track_width) + std::fabs(p->oob_offset)) * 1.02 + 16.0);
+        // ... and that keep one step's increment inside the 1.5 * 2^23 rounding trick (|increment| < 2^22 units) for
+        // speeds up to 16 m/s, three times what the boat model reaches (the observation range of v_x ends at 5 m/s)
+        int inc_shift = 30;
+        while (inc_shift > 0 && 16.0 * p->dt * (double)(1LL << inc_shift) >= 4194304.0) --inc_shift;
+        f.sx_shift = std::min(inc_shift, shift_for(std::fabs(p->goal_line) * 1.02 + 16.0));
+        f.sy_shift = std::min(inc_shift, shift_for((std::fabs(p->track_width) + std::fabs(p->oob_offset)) * 1.02 + 16.0));
         f.sx_k = (float)(p->dt * (double)(1LL << f.sx_shift));
         f.sy_k = (float)(p->dt * (double)(1LL << f.sy_shift));
         f.sx_inv = (float)(1.0 / (double)(1LL << f.sx_shift));
