@@ -225,10 +225,12 @@ def cpu_baseline_leg(target_seconds: float = 10.0) -> dict:
     one = ref_bench.measure(1, 4.0, EXPERIMENT, SEED)
     return {"value": allc["value"], "unit": UNIT, "cores": cores, "kind": "reference",
             "sample": f"unmodified reference BoatEnv (environment/boat_env.py under oracle/ref_shim.py stubs), experiment "
-                      f"{EXPERIMENT}, {cores} processes x 1 env, float32 uniform(-1,1) actions, resets included: "
+                      f"{EXPERIMENT}, {cores} processes x 1 env, float32-representable uniform(-1,1) actions as float64, resets included: "
                       f"{allc['steps']} env-steps in {allc['seconds']:.1f} s ({allc['episodes']} episodes)",
             "value_1core": one["value"],
             "sample_1core": f"1 process: {one['steps']} env-steps in {one['seconds']:.1f} s",
+            # the names BASELINE.md section 3 announces
+            "cpu_steps_per_s_1core": one["value"], "cpu_steps_per_s_allcores": allc["value"], "cpu_cores": cores,
             "port": port}
 
 
@@ -255,8 +257,8 @@ def run_reference(args) -> None:
         pool.close()
         kind = "reference"
         sample = (f"each step = {cores} processes x 1 env x {per_proc} env-steps of the UNMODIFIED reference BoatEnv "
-                  f"(environment/boat_env.py, staged by oracle/make_ref.py), experiment {EXPERIMENT}, float32 uniform(-1,1) "
-                  f"actions, resets included ({episodes} episodes in the timed steps)")
+                  f"(environment/boat_env.py, staged by oracle/make_ref.py), experiment {EXPERIMENT}, float32-representable uniform(-1,1) "
+                  f"actions as float64, resets included ({episodes} episodes in the timed steps)")
         ran = {"implementation": "reference BoatEnv (Python, unmodified)", "processes": cores, "envs": cores,
                "env_steps_per_process_per_step": per_proc, "experiment": EXPERIMENT, "precision": "fp64 (numpy scalars)"}
     else:

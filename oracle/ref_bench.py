@@ -3,7 +3,7 @@
 TEST / MEASUREMENT INFRASTRUCTURE ONLY (bench.py's ``cpu_baseline`` leg and ``--impl reference`` arm).  Every
 worker process imports the UNMODIFIED reference ``BoatEnv`` (environment/boat_env.py:9) from ``/root/reference`` or
 from the staged copy ``oracle/_ref`` (oracle/make_ref.py) under the stub modules of ``oracle/ref_shim.py`` and runs
-the loop of main.py:70-99 without the agent: ``reset()``; ``step(action)`` with float32 uniform(-1,1) actions
+the loop of main.py:70-99 without the agent: ``reset()``; ``step(action)`` with float32-representable uniform(-1,1) actions
 (policy A1 of SURVEY.md 8d); ``reset()`` again when done.  One env per process -- the reference's own fan-out
 style (main.py:215-235 starts one Process per model).
 """
@@ -35,7 +35,9 @@ def _worker_run(n_steps: int):
     """n_steps env-steps of the reference loop (resets included in the time).  Returns (steps, seconds, episodes)."""
     import numpy as np
     env, rng = _ENV, _RNG
-    acts = rng.uniform(-1.0, 1.0, size=n_steps).astype(np.float32)
+    # float32-representable actions passed as float64 (BASELINE.md section 3, SURVEY.md H4: a float32 action would make
+    # the reference accumulate its rudder in float32)
+    acts = rng.uniform(-1.0, 1.0, size=n_steps).astype(np.float32).astype(np.float64)
     episodes = 0
     t0 = time.perf_counter()
     for k in range(n_steps):
