@@ -142,6 +142,20 @@ def test_l2_resident_population_sampled_parity(S, O, precision, n):
     env.close()
 
 
+@pytest.mark.parametrize("experiment", [1, 3, 4, 5])
+def test_other_experiments_sampled_parity_at_scale(S, O, experiment):
+    """The other kernel instantiations (no wind, constant wind, one random curve as velocity / as rectified direction)
+    at 4 M envs, fp32, the same sampled comparison: experiments 4 and 5 use the warp-specialised setup path with
+    one curve, 1 and 3 the inline path without curves."""
+    cfg = S.load_config(base_settings__experiment=experiment)
+    n = 4 * 1024 * 1024 + 11
+    ids = sample_ids(n, 2500, seed=10 + experiment)
+    env = S.BatchedBoatEnv(cfg, n, seed=4, precision="fp32", device=0, auto_reset=True)
+    out, ref, d = compare_with_oracle(S, O, cfg, env, ids, 420, 24, "fp32", lambda e, a: e.step(a))
+    assert scaled_err(out["final_obs"][d], ref["obs"][d]).max() <= TOL["fp32"]
+    env.close()
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp64"])
 def test_full_population_fused_store_sampled_parity(S, O, precision):
     """boatenv_step_store (step + agent.remember in one kernel) at 4 M envs over a 6 M-slot ring (wraps twice):
