@@ -170,6 +170,48 @@ def test_shard_range_tiles_population(S):
         S.shard_range(10, 2, 2)
 
 
+def test_host_batch_draws_equal_the_per_pair_draws(S):
+    """boatenv_episode_draws_batch_host == boatenv_episode_draws_host for every (env, episode) of the batch."""
+    L = S.lib()
+    p = S.params_from_config(S.load_config(base_settings__experiment=6))
+    ids = np.array([0, 1, 31, 32, 12345, 2 ** 33 + 7], dtype=np.int64)
+    E, e0 = 5, 3
+    s_y = np.empty((E, len(ids)), dtype=np.int32)
+    knots = np.empty((E, len(ids), 2, 8))
+    assert L.boatenv_episode_draws_batch_host(C.byref(p), 9, ids.ctypes.data, len(ids), e0, E, s_y.ctypes.data,
+                                              knots.ctypes.data) == 0
+    for e in range(E):
+        for j, g in enumerate(ids):
+            s = C.c_int32()
+            k = (C.c_double * 16)()
+            assert L.boatenv_episode_draws_host(C.byref(p), 9, int(g), e0 + e, C.byref(s), k) == 0
+            assert s.value == s_y[e, j] and np.array_equal(np.array(k[:]).reshape(2, 8), knots[e, j])
+    assert L.boatenv_episode_draws_batch_host(C.byref(p), 9, None, 1, 0, 1, None, None) == -1
+    neg = np.array([-1], dtype=np.int64)
+    assert L.boatenv_episode_draws_batch_host(C.byref(p), 9, neg.ctypes.data, 1, 0, 1, s_y.ctypes.data, None) == -1
+
+
+def test_host_toy_parameters(S):
+    """boattoy_params_host: env 0 keeps the script constants (toy_car.py:7-8,11,23; toy_parachute.py:8-15), every
+    other env gets each constant times (1 + jitter * u), u in [-1, 1) from Philox(seed, env, parameter)."""
+    L = S.lib()
+    car = np.array([10.0, 10.0, 0.01, 0.1])
+    out = np.empty((1000, 4))
+    arr = (C.c_double * 4)(*car)
+    assert L.boattoy_params_host(0, arr, 4, 0.1, 3, 0, 1000, out.ctypes.data) == 0
+    assert np.array_equal(out[0], car) and np.all(np.abs(out[1:] / car - 1.0) <= 0.1)
+    assert np.unique(out[:, 0]).size > 990 and abs((out[1:, 0] / 10.0 - 1.0).mean()) < 0.01
+    again = np.empty((10, 4))
+    assert L.boattoy_params_host(0, arr, 4, 0.1, 3, 500, 10, again.ctypes.data) == 0
+    assert np.array_equal(again, out[500:510])                       # a pure function of (seed, env, parameter)
+    other = np.empty((10, 4))
+    assert L.boattoy_params_host(0, arr, 4, 0.1, 4, 500, 10, other.ctypes.data) == 0 and not np.array_equal(other, again)
+    flat = np.empty((5, 4))
+    assert L.boattoy_params_host(0, arr, 4, 0.0, 3, 0, 5, flat.ctypes.data) == 0 and np.all(flat == car)
+    assert L.boattoy_params_host(0, arr, 9, 0.1, 3, 0, 5, flat.ctypes.data) == -1     # wrong parameter count for a car
+    assert L.boattoy_params_host(7, arr, 4, 0.1, 3, 0, 5, flat.ctypes.data) == -1     # unknown toy
+
+
 _WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})

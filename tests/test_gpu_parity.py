@@ -526,6 +526,39 @@ def test_single_env_drop_in(S, O):
     env.close()
 
 
+@pytest.mark.parametrize("stream", ["A1", "A2", "A3"])
+def test_config0_single_env_action_streams(S, O, stream):
+    """BASELINE.json configs[0] / SURVEY.md 8(d) config 1: experiment 1, ONE env (the reference's own use), one
+    episode of fixed random actions from np.random.default_rng(0), through the single-env drop-in `BoatEnv`:
+    A1 float32(U(-1,1)) (ends by rudder_broken after a few hundred steps), A2 float32(0.05 U(-1,1)) (thousands of
+    steps), A3 zeros with test_mode = 1 (fixture 1: reached_goal after 4959 steps).  Step count, termination and
+    every observation / reward against the oracle (fp64: 1e-9)."""
+    over = dict(base_settings__experiment=1)
+    if stream == "A3":
+        over["base_settings__test_mode"] = 1
+    cfg = S.load_config(**over)
+    env = S.BoatEnv(cfg, experiment=None, seed=0, precision="fp64", device=0)
+    o = O.OracleEnv(O.params_from_config(cfg))
+    obs, ref = env.reset(), o.reset(0)
+    assert np.array_equal(obs, ref)
+    rng = np.random.default_rng(0)
+    scale = {"A1": 1.0, "A2": 0.05, "A3": 0.0}[stream]
+    steps, done, total = 0, False, 0.0
+    while not done and steps < 10001:
+        a = np.array([np.float32(scale * rng.uniform(-1, 1))], dtype=np.float64)   # float32-representable, passed as float64 (H4)
+        obs, reward, done, info = env.step(a)
+        ro, rr, rd, rc = o.step(float(a[0]))
+        steps += 1
+        total += reward
+        assert done == rd and scaled_err(obs, ro).max() <= TOL64 and abs(reward - rr) <= TOL64 * max(1.0, abs(rr)), steps
+    assert done and info["termination"] == O.TERM_NAMES[rc] and info["episode_reward"] == pytest.approx(total)
+    if stream == "A1":
+        assert info["termination"] == "rudder_broken" and 20 < steps < 3000
+    if stream == "A3":
+        assert info["termination"] == "reached_goal" and steps == 4959
+    env.close()
+
+
 def test_full_size_properties(S):
     """BASELINE.json configs[2] shape (exp 6, fp32, millions of envs): properties that do
     not need the oracle -- determinism, counter consistency, fuel bookkeeping."""
