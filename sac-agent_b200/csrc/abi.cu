@@ -656,7 +656,10 @@ int boatenv_env_state_host(boatenv_t h, int64_t env_index, double *out_host) {
     int rc = ensure_host_path(h);
     if (!rc) rc = ensure_zero_copy(h);
     if (rc) return rc;
-    CUDA_TRY(cudaDeviceSynchronize());  // after whatever the caller queued on its own streams
+    // ordered after the work queued on the legacy default stream (what the single-env drop-in uses): an event wait,
+    // not a device-wide synchronise
+    CUDA_TRY(cudaEventRecord(h->ev_caller, nullptr));
+    CUDA_TRY(cudaStreamWaitEvent(h->compute, h->ev_caller, 0));
     double *dev = reinterpret_cast<double *>(h->zc_dev + h->zc_fields);
     CUDA_TRY(h->precision == 32 ? launch_env_state_f32(h->cfg, env_index, dev, h->compute)
                                 : launch_env_state_f64(h->cfg, env_index, dev, h->compute));
